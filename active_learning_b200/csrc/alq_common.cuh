@@ -1,0 +1,160 @@
+// Shared device/host helpers for libalq (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <initializer_list>
+#include <string>
+#include <vector>
+
+#include "../../include/alq.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libalq is written for sm_100a (B200) only"
+#endif
+
+struct alq_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t side_stream = nullptr;   // H2D pipelining for the *_host entry points
+    cudaStream_t side_stream2 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // grow-only scratch arenas (device) and pinned host staging
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* arena2 = nullptr;               // buffers of the *_host entry points
+    size_t arena2_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    int64_t launches = 0;
+    std::string err;
+};
+
+#define ALQ_FAIL(ctx, code, ...)                                   \
+    do {                                                           \
+        char _b[512];                                              \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                     \
+        (ctx)->err = _b;                                           \
+        return (code);                                             \
+    } while (0)
+
+#define ALQ_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ALQ_FAIL(ctx, ALQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                  \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+        }                                                                                \
+    } while (0)
+
+#define ALQ_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess) {                                                         \
+            ALQ_FAIL(ctx, ALQ_ERR_CUDA, "kernel launch failed: %s (%s:%d)",              \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+        }                                                                                \
+    } while (0)
+
+// Device scratch: returns a 256-byte aligned pointer into the arena, growing it if needed.
+int alq_scratch_reserve(alq_ctx* ctx, size_t bytes);
+int alq_pinned_reserve(alq_ctx* ctx, size_t bytes);
+int alq_arena2_reserve(alq_ctx* ctx, size_t bytes);
+
+struct ScratchCursor {
+    char* base;
+    size_t off = 0;
+    explicit ScratchCursor(void* b) : base(static_cast<char*>(b)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+static inline size_t scratch_need(std::initializer_list<size_t> sizes) {
+    size_t t = 0;
+    for (size_t s : sizes) t = ((t + 255) & ~size_t(255)) + s;
+    return t + 256;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#define ALQ_NEG_INF (__int_as_float(0xff800000))
+#define ALQ_POS_INF (__int_as_float(0x7f800000))
+
+// Monotone float -> uint32 map: a < b  <=>  ord(a) < ord(b)   (-0.0 sorts just below +0.0).
+__host__ __device__ __forceinline__ uint32_t alq_ord(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float alq_unord(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// arg-max key: larger value wins, equal values -> lower row wins.
+__device__ __forceinline__ unsigned long long alq_maxkey(float v, uint32_t row) {
+    return (static_cast<unsigned long long>(alq_ord(v)) << 32) | (0xffffffffu - row);
+}
+__host__ __device__ __forceinline__ uint32_t alq_maxkey_row(unsigned long long k) {
+    return 0xffffffffu - static_cast<uint32_t>(k & 0xffffffffu);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+// streaming 128-bit load that does not pollute L1 (data is read exactly once per launch)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// float atomic min/max that is correct across signs (IEEE ordering trick).
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

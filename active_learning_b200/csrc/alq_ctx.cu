@@ -1,0 +1,99 @@
+// Context, scratch arenas and error reporting of libalq.
+#include <initializer_list>
+#include <new>
+
+#include "alq_common.cuh"
+
+extern "C" int alq_version(void) { return 1; }
+
+extern "C" int alq_create(alq_ctx** out, int device) {
+    if (!out) return ALQ_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ALQ_ERR_CUDA;  // no CPU fallback: without a usable GPU there is no context
+    }
+    alq_ctx* ctx = new (std::nothrow) alq_ctx();
+    if (!ctx) return ALQ_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return ALQ_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        delete ctx;
+        return ALQ_ERR_CUDA;  // built for sm_100a only
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking);
+    cudaEventCreate(&ctx->ev_a);
+    cudaEventCreate(&ctx->ev_b);
+    *out = ctx;
+    return ALQ_OK;
+}
+
+extern "C" void alq_destroy(alq_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->arena2) cudaFree(ctx->arena2);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->side_stream2) cudaStreamDestroy(ctx->side_stream2);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    delete ctx;
+}
+
+extern "C" const char* alq_last_error(const alq_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int64_t alq_launch_count(const alq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int alq_scratch_reserve(alq_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return ALQ_OK;
+    // grow-only; callers never hold scratch pointers across API calls
+    ALQ_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    size_t want = bytes + (bytes >> 2) + (1u << 20);
+    if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) {
+        cudaGetLastError();
+        ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "scratch allocation of %zu bytes failed", want);
+    }
+    ctx->scratch_bytes = want;
+    return ALQ_OK;
+}
+
+int alq_pinned_reserve(alq_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return ALQ_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    if (cudaMallocHost(&ctx->pinned, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
+    }
+    ctx->pinned_bytes = bytes;
+    return ALQ_OK;
+}
+
+int alq_arena2_reserve(alq_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->arena2_bytes) return ALQ_OK;
+    ALQ_CUDA(ctx, cudaDeviceSynchronize());
+    if (ctx->arena2) cudaFree(ctx->arena2);
+    ctx->arena2 = nullptr;
+    ctx->arena2_bytes = 0;
+    if (cudaMalloc(&ctx->arena2, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "arena2 allocation of %zu bytes failed", bytes);
+    }
+    ctx->arena2_bytes = bytes;
+    return ALQ_OK;
+}

@@ -1,0 +1,428 @@
+// K1 (softmax-uncertainty scores), K2 (BADGE gradient-embedding factors), K2p (pooled embedding)
+// and row norms.  All are one-pass HBM-streaming kernels: one warp owns one row, the row lives in
+// registers between the max pass and the exp pass, loads are 128-bit and L1-bypassing.
+//
+// Reference semantics: margin_sampler.py:33-35, confidence_sampler.py:31-33,
+// badge_sampler.py:33-44, coreset_sampler.py:61 (all under /root/reference/src/query_strategies).
+#include <initializer_list>
+
+#include "alq_common.cuh"
+
+namespace {
+
+constexpr int kScoreThreads = 256;
+
+struct RowStats {
+    float m;    // max logit
+    float t2;   // second largest logit (== m when the max is repeated)
+    float s;    // sum exp(z - m)
+    float w;    // sum exp(z - m) * (z - m)      (entropy only)
+    int arg;    // lowest index attaining m       (BADGE only)
+};
+
+__device__ __forceinline__ void top2_push(float v, float& t1, float& t2) {
+    if (v > t1) { t2 = t1; t1 = v; }
+    else if (v > t2) t2 = v;
+}
+
+// Row held as NV float4 per lane (vector path) --------------------------------------------------
+template <int NV, bool WANT_ARG, bool WANT_W>
+__device__ __forceinline__ RowStats row_stats_vec(const float4 (&v)[NV], int lane, int nvec) {
+    float t1 = ALQ_NEG_INF, t2 = ALQ_NEG_INF;
+    int arg = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int base = (lane + 32 * k) * 4;
+        if (lane + 32 * k < nvec) {
+            const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (WANT_ARG && e[j] > t1) arg = base + j;   // strict: first occurrence wins
+                top2_push(e[j], t1, t2);
+            }
+        }
+    }
+    // merge (t1,t2[,arg]) across the warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float o1 = __shfl_xor_sync(0xffffffffu, t1, o);
+        const float o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+        if (WANT_ARG) {
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (o1 > t1 || (o1 == t1 && oa < arg)) arg = oa;
+        }
+        const float hi = fmaxf(t1, o1);
+        t2 = fmaxf(fminf(t1, o1), fmaxf(t2, o2));
+        t1 = hi;
+    }
+    float s = 0.f, w = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        if (lane + 32 * k < nvec) {
+            const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dz = e[j] - t1;
+                const float ex = expf(dz);
+                s += ex;
+                if (WANT_W) w += ex * dz;
+            }
+        }
+    }
+    s = warp_sum(s);
+    if (WANT_W) w = warp_sum(w);
+    return RowStats{t1, t2, s, w, arg};
+}
+
+__device__ __forceinline__ float score_from_stats(const RowStats& r, int mode) {
+    if (mode == ALQ_MODE_MARGIN) {
+        // p(1) - p(2) with p = exp(z - max) / sum, each quotient rounded like torch's softmax
+        return 1.0f / r.s - expf(r.t2 - r.m) / r.s;
+    }
+    if (mode == ALQ_MODE_LEAST_CONFIDENCE) return 1.0f / r.s;
+    // sum_c p_c log p_c = (sum e*(z-m))/s - log s
+    float sc = r.w / r.s - logf(r.s);
+    return sc + 0.0f;  // canonical +0
+}
+
+template <int NV, int MODE>
+__global__ void __launch_bounds__(kScoreThreads)
+score_rows_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld,
+                      float* __restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int nvec = c >> 2;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        const float4* p = reinterpret_cast<const float4*>(logits + row * ld);
+        float4 v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < nvec) v[k] = ld_stream_f4(p + idx);
+        }
+        const RowStats r = row_stats_vec<NV, false, MODE == ALQ_MODE_ENTROPY>(v, lane, nvec);
+        if (lane == 0) scores[row] = score_from_stats(r, MODE);
+    }
+}
+
+// Any c / alignment: two passes over the row, the second one hits L1/L2.
+__global__ void __launch_bounds__(kScoreThreads)
+score_rows_generic_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int mode,
+                          float* __restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        const float* p = logits + row * ld;
+        float t1 = ALQ_NEG_INF, t2 = ALQ_NEG_INF;
+        for (int j = lane; j < c; j += 32) top2_push(p[j], t1, t2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float o1 = __shfl_xor_sync(0xffffffffu, t1, o);
+            const float o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+            const float hi = fmaxf(t1, o1);
+            t2 = fmaxf(fminf(t1, o1), fmaxf(t2, o2));
+            t1 = hi;
+        }
+        float s = 0.f, w = 0.f;
+        for (int j = lane; j < c; j += 32) {
+            const float dz = p[j] - t1;
+            const float ex = expf(dz);
+            s += ex;
+            w += ex * dz;
+        }
+        s = warp_sum(s);
+        w = warp_sum(w);
+        if (lane == 0) scores[row] = score_from_stats(RowStats{t1, t2, s, w, 0}, mode);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: a = (softmax - onehot(argmax)) * (1 / bs_i)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float batch_scale(int64_t row, int64_t n, int bs) {
+    const int64_t tail = n % bs;
+    const int64_t cut = n - tail;
+    return 1.0f / static_cast<float>(row < cut ? bs : static_cast<int>(tail));
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kScoreThreads)
+badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs,
+                         float* __restrict__ a, int64_t lda, float* __restrict__ a_norm2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int nvec = c >> 2;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        const float4* p = reinterpret_cast<const float4*>(logits + row * ld);
+        float4 v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < nvec) v[k] = ld_stream_f4(p + idx);
+        }
+        const RowStats r = row_stats_vec<NV, true, false>(v, lane, nvec);
+        const float inv_bs = batch_scale(row, n, bs);
+        float4* q = reinterpret_cast<float4*>(a + row * lda);
+        float nn = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < nvec) {
+                float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float pj = expf(e[j] - r.m) / r.s;
+                    const float g = (pj - ((idx * 4 + j) == r.arg ? 1.0f : 0.0f)) * inv_bs;
+                    e[j] = g;
+                    nn += g * g;
+                }
+                q[idx] = make_float4(e[0], e[1], e[2], e[3]);
+            }
+        }
+        nn = warp_sum(nn);
+        if (lane == 0) a_norm2[row] = nn;
+    }
+}
+
+__global__ void __launch_bounds__(kScoreThreads)
+badge_factors_generic_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs,
+                             float* __restrict__ a, int64_t lda, int cpad,
+                             float* __restrict__ a_norm2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        const float* p = logits + row * ld;
+        float m = ALQ_NEG_INF;
+        int arg = 0x7fffffff;
+        for (int j = lane; j < c; j += 32) {
+            const float z = p[j];
+            if (z > m) { m = z; arg = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+        }
+        float s = 0.f;
+        for (int j = lane; j < c; j += 32) s += expf(p[j] - m);
+        s = warp_sum(s);
+        const float inv_bs = batch_scale(row, n, bs);
+        float nn = 0.f;
+        for (int j = lane; j < cpad; j += 32) {
+            float g = 0.f;
+            if (j < c) g = (expf(p[j] - m) / s - (j == arg ? 1.0f : 0.0f)) * inv_bs;
+            a[row * lda + j] = g;
+            nn += g * g;
+        }
+        nn = warp_sum(nn);
+        if (lane == 0) a_norm2[row] = nn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2p: pooled gradient embedding out[i, r*pw + s] = mean_{bin r}(a_i) * mean_{bin s}(h_i)
+// (adaptive_avg_pool2d of a rank-1 matrix is the outer product of the 1-D pools).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPoolWarps = 4;
+
+__global__ void __launch_bounds__(kPoolWarps * 32)
+badge_pooled_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs,
+                    const float* __restrict__ emb, int d, int64_t lde, int ph, int pw,
+                    float* __restrict__ out, int64_t ldo) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    float* sa = smem + static_cast<size_t>(wib) * (c + ph + pw);
+    float* spa = sa + c;
+    float* sph = spa + ph;
+    const int64_t warp = static_cast<int64_t>(blockIdx.x) * kPoolWarps + wib;
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kPoolWarps;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        const float* p = logits + row * ld;
+        float m = ALQ_NEG_INF;
+        int arg = 0x7fffffff;
+        for (int j = lane; j < c; j += 32) {
+            const float z = p[j];
+            if (z > m) { m = z; arg = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+        }
+        float s = 0.f;
+        for (int j = lane; j < c; j += 32) s += expf(p[j] - m);
+        s = warp_sum(s);
+        const float inv_bs = batch_scale(row, n, bs);
+        for (int j = lane; j < c; j += 32)
+            sa[j] = (expf(p[j] - m) / s - (j == arg ? 1.0f : 0.0f)) * inv_bs;
+        __syncwarp();
+        for (int r = lane; r < ph; r += 32) {
+            const int lo = static_cast<int>((static_cast<int64_t>(r) * c) / ph);
+            const int hi = static_cast<int>((static_cast<int64_t>(r + 1) * c + ph - 1) / ph);
+            float acc = 0.f;
+            for (int j = lo; j < hi; ++j) acc += sa[j];
+            spa[r] = acc / static_cast<float>(hi - lo);
+        }
+        const float* h = emb + row * lde;
+        for (int q = lane; q < pw; q += 32) {
+            const int lo = static_cast<int>((static_cast<int64_t>(q) * d) / pw);
+            const int hi = static_cast<int>((static_cast<int64_t>(q + 1) * d + pw - 1) / pw);
+            float acc = 0.f;
+            for (int j = lo; j < hi; ++j) acc += h[j];
+            sph[q] = acc / static_cast<float>(hi - lo);
+        }
+        __syncwarp();
+        float* o = out + row * ldo;
+        for (int k = lane; k < ph * pw; k += 32) o[k] = spa[k / pw] * sph[k % pw];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row norms
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScoreThreads)
+row_norm2_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ld, int vec,
+                 float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp; row < n; row += nwarps) {
+        float acc = 0.f;
+        if (vec) {
+            const float4* p = reinterpret_cast<const float4*>(x + row * ld);
+            for (int k = lane; k < (d >> 2); k += 32) {
+                const float4 v = ld_stream_f4(p + k);
+                acc += v.x * v.x;
+                acc += v.y * v.y;
+                acc += v.z * v.z;
+                acc += v.w * v.w;
+            }
+        } else {
+            const float* p = x + row * ld;
+            for (int k = lane; k < d; k += 32) acc += p[k] * p[k];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[row] = acc;
+    }
+}
+
+int rows_grid(const alq_ctx* ctx, int64_t n, int warps_per_block) {
+    int64_t need = (n + warps_per_block - 1) / warps_per_block;
+    int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
+    if (need < 1) need = 1;
+    return static_cast<int>(need < cap ? need : cap);
+}
+
+template <int NV>
+void launch_score_vec(int mode, int grid, cudaStream_t st, const float* logits, int64_t n, int c,
+                      int64_t ld, float* scores) {
+    if (mode == ALQ_MODE_MARGIN)
+        score_rows_vec_kernel<NV, ALQ_MODE_MARGIN><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, scores);
+    else if (mode == ALQ_MODE_LEAST_CONFIDENCE)
+        score_rows_vec_kernel<NV, ALQ_MODE_LEAST_CONFIDENCE><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, scores);
+    else
+        score_rows_vec_kernel<NV, ALQ_MODE_ENTROPY><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, scores);
+}
+
+}  // namespace
+
+extern "C" int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
+                                 int32_t mode, float* scores, void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (n < 0 || c <= 0 || ld < c || mode < 0 || mode > 2)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_score_softmax: bad shape n=%lld c=%d ld=%lld mode=%d",
+                 (long long)n, c, (long long)ld, mode);
+    if (n == 0) return ALQ_OK;
+    if (!logits || !scores) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_score_softmax: null pointer");
+    if (n >= (1LL << 31)) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_score_softmax: n must be < 2^31");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = rows_grid(ctx, n, kScoreThreads / 32);
+    const bool vec = (c % 4 == 0) && (ld % 4 == 0) && aligned16(logits) && c <= 2048;
+    if (vec) {
+        const int nv = (c / 4 + 31) / 32;
+        if (nv <= 1) launch_score_vec<1>(mode, grid, st, logits, n, c, ld, scores);
+        else if (nv <= 2) launch_score_vec<2>(mode, grid, st, logits, n, c, ld, scores);
+        else if (nv <= 4) launch_score_vec<4>(mode, grid, st, logits, n, c, ld, scores);
+        else if (nv <= 8) launch_score_vec<8>(mode, grid, st, logits, n, c, ld, scores);
+        else launch_score_vec<16>(mode, grid, st, logits, n, c, ld, scores);
+    } else {
+        score_rows_generic_kernel<<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, mode, scores);
+    }
+    ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}
+
+extern "C" int alq_badge_factors(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
+                                 int32_t batch_size, float* a, int64_t lda, float* a_norm2,
+                                 void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    const int cpad = (c + 3) & ~3;
+    if (n < 0 || c <= 0 || ld < c || lda < cpad || batch_size <= 0)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_badge_factors: bad shape n=%lld c=%d ld=%lld lda=%lld bs=%d",
+                 (long long)n, c, (long long)ld, (long long)lda, batch_size);
+    if (n == 0) return ALQ_OK;
+    if (!logits || !a || !a_norm2) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_badge_factors: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = rows_grid(ctx, n, kScoreThreads / 32);
+    const bool vec = (c % 4 == 0) && (ld % 4 == 0) && (lda % 4 == 0) && aligned16(logits) &&
+                     aligned16(a) && c <= 2048;
+    if (vec) {
+        const int nv = (c / 4 + 31) / 32;
+        if (nv <= 1) badge_factors_vec_kernel<1><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
+        else if (nv <= 2) badge_factors_vec_kernel<2><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
+        else if (nv <= 4) badge_factors_vec_kernel<4><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
+        else if (nv <= 8) badge_factors_vec_kernel<8><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
+        else badge_factors_vec_kernel<16><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
+    } else {
+        badge_factors_generic_kernel<<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda,
+                                                                    cpad, a_norm2);
+    }
+    ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}
+
+extern "C" int alq_badge_pooled_embedding(alq_ctx* ctx, const float* logits, int64_t n, int32_t c,
+                                          int64_t ld, int32_t batch_size, const float* emb, int32_t d,
+                                          int64_t lde, float* out, int64_t ldo, void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    const int ph = c < 16 ? c : 16;          // badge_sampler.py:42  min(POOLING_H, C)
+    const int pw = 512 / ph;                 // badge_sampler.py:43  int(POOLING_AREA / pool_h)
+    if (n < 0 || c <= 0 || d <= 0 || ld < c || lde < d || ldo < ph * pw || batch_size <= 0 || pw > d)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_badge_pooled_embedding: bad shape n=%lld c=%d d=%d",
+                 (long long)n, c, d);
+    if (n == 0) return ALQ_OK;
+    if (!logits || !emb || !out) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_badge_pooled_embedding: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = static_cast<size_t>(kPoolWarps) * (c + ph + pw) * sizeof(float);
+    if (smem > ctx->smem_optin)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_badge_pooled_embedding: c=%d too large for shared memory", c);
+    if (smem > 48 * 1024)
+        ALQ_CUDA(ctx, cudaFuncSetAttribute(badge_pooled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+    const int grid = rows_grid(ctx, n, kPoolWarps);
+    badge_pooled_kernel<<<grid, kPoolWarps * 32, smem, st>>>(logits, n, c, ld, batch_size, emb, d, lde,
+                                                           ph, pw, out, ldo);
+    ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}
+
+extern "C" int alq_row_norm2(alq_ctx* ctx, const float* x, int64_t n, int32_t d, int64_t ld, float* out,
+                             void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (n < 0 || d <= 0 || ld < d) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_row_norm2: bad shape");
+    if (n == 0) return ALQ_OK;
+    if (!x || !out) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_row_norm2: null pointer");
+    const int vec = (d % 4 == 0) && (ld % 4 == 0) && aligned16(x);
+    const int grid = rows_grid(ctx, n, kScoreThreads / 32);
+    row_norm2_kernel<<<grid, kScoreThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, d, ld, vec, out);
+    ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}

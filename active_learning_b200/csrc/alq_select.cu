@@ -1,0 +1,385 @@
+// K1b: positions of the B smallest scores in ascending (score, position) order -- the device
+// replacement of `torch.sort(scores).indices[:B]` (margin_sampler.py:42, confidence_sampler.py:42
+// under /root/reference/src/query_strategies) with the fixed tie-break "lowest position first".
+//
+//   1. 3-level MSB radix select (11+11+10 bits) over the order-preserving uint32 image of the
+//      scores finds T, the B-th smallest key, and how many keys tie with it inside the budget.
+//   2. One counting pass + one writing pass compact {key < T} (any order) and the first ties
+//      {key == T} in position order into B 64-bit keys (key << 32 | position).
+//   3. A bitonic network sorts those B keys (single CTA in shared memory for B <= 16384).
+//
+// Work is O(N) reads of 4 bytes per level: 4*N*5 bytes in total, negligible next to K1's 4*C*N.
+#include <initializer_list>
+
+#include "alq_common.cuh"
+
+namespace {
+
+constexpr int kSelThreads = 256;
+constexpr int kSelItems = 8;                       // consecutive positions per thread
+constexpr int kSelChunk = kSelThreads * kSelItems; // positions per block in the compaction passes
+constexpr int kBins = 2048;
+
+struct SelState {
+    unsigned long long k;     // 1-based rank still to resolve inside the current prefix
+    uint32_t prefix;          // resolved high bits of T
+    uint32_t ticket;          // last-block election
+    uint32_t lt_counter;      // slots handed out to keys < T
+    uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t score_key(float s) { return alq_ord(s + 0.0f); }
+
+// LEVEL 0: bits 31..21, LEVEL 1: bits 20..10, LEVEL 2: bits 9..0
+template <int LEVEL>
+__global__ void __launch_bounds__(kSelThreads)
+select_hist_kernel(const float* __restrict__ scores, int64_t n, SelState* st, uint32_t* hist) {
+    __shared__ uint32_t sh[kBins];
+    __shared__ unsigned long long part[kSelThreads];
+    __shared__ bool last;
+    for (int i = threadIdx.x; i < kBins; i += kSelThreads) sh[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = st->prefix;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kSelThreads;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kSelThreads + threadIdx.x; i < n; i += stride) {
+        const uint32_t key = score_key(scores[i]);
+        if (LEVEL == 0) atomicAdd(&sh[key >> 21], 1u);
+        else if (LEVEL == 1) { if ((key >> 21) == prefix) atomicAdd(&sh[(key >> 10) & 0x7ffu], 1u); }
+        else { if ((key >> 10) == prefix) atomicAdd(&sh[key & 0x3ffu], 1u); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBins; i += kSelThreads)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // the last block resolves this level: find the bin holding rank k
+    unsigned long long mine[kBins / kSelThreads];
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int j = 0; j < kBins / kSelThreads; ++j) {
+        mine[j] = __ldcg(&hist[threadIdx.x * (kBins / kSelThreads) + j]);
+        tot += mine[j];
+    }
+    part[threadIdx.x] = tot;
+    __syncthreads();
+    for (int off = 1; off < kSelThreads; off <<= 1) {  // inclusive Hillis-Steele scan
+        unsigned long long v = threadIdx.x >= off ? part[threadIdx.x - off] : 0ull;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned long long k = st->k;
+    const unsigned long long incl = part[threadIdx.x];
+    const unsigned long long excl = incl - tot;
+    __syncthreads();
+    if (excl < k && k <= incl) {
+        unsigned long long run = excl;
+#pragma unroll
+        for (int j = 0; j < kBins / kSelThreads; ++j) {
+            if (run < k && k <= run + mine[j]) {
+                const uint32_t bin = threadIdx.x * (kBins / kSelThreads) + j;
+                st->prefix = LEVEL == 2 ? ((prefix << 10) | bin) : ((prefix << 11) | bin);
+                st->k = k - run;
+            }
+            run += mine[j];
+        }
+    }
+    for (int i = threadIdx.x; i < kBins; i += kSelThreads) hist[i] = 0;
+    if (threadIdx.x == 0) st->ticket = 0;
+}
+
+// Counting pass: ties with T per chunk, then (last block) exclusive offsets.
+__global__ void __launch_bounds__(kSelThreads)
+select_count_kernel(const float* __restrict__ scores, int64_t n, SelState* st,
+                    uint32_t* __restrict__ eq_count, int nblocks) {
+    __shared__ uint32_t wsum[kSelThreads / 32];
+    __shared__ bool last;
+    const uint32_t T = st->prefix;
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kSelChunk + threadIdx.x * kSelItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < kSelItems; ++j)
+        if (base + j < n) c += (score_key(scores[base + j]) == T);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) t += wsum[w];
+        eq_count[blockIdx.x] = t;
+        __threadfence();
+        last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {  // one warp turns counts into exclusive offsets, 32 blocks at a time
+        uint32_t carry = 0;
+        for (int b0 = 0; b0 < nblocks; b0 += 32) {
+            const int b = b0 + threadIdx.x;
+            const uint32_t v = b < nblocks ? __ldcg(&eq_count[b]) : 0u;
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (threadIdx.x >= o) inc += u;
+            }
+            if (b < nblocks) eq_count[b] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) st->ticket = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_write_kernel(const float* __restrict__ scores, int64_t n, int64_t b, SelState* st,
+                    const uint32_t* __restrict__ eq_off, unsigned long long* __restrict__ keys) {
+    __shared__ uint32_t wsum[kSelThreads / 32];
+    const uint32_t T = st->prefix;
+    const unsigned long long ties = st->k;                 // ties taken inside the budget
+    const unsigned long long n_less = static_cast<unsigned long long>(b) - ties;
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kSelChunk + threadIdx.x * kSelItems;
+    uint32_t key[kSelItems];
+    uint32_t eq = 0;
+#pragma unroll
+    for (int j = 0; j < kSelItems; ++j) {
+        key[j] = base + j < n ? score_key(scores[base + j]) : 0xffffffffu;
+        if (base + j < n && key[j] == T) ++eq;
+    }
+    // block-exclusive scan of the per-thread tie counts (threads own consecutive positions)
+    uint32_t inc = eq;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += u;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += wsum[w];
+    unsigned long long rank = static_cast<unsigned long long>(eq_off[blockIdx.x]) + woff + inc - eq;
+#pragma unroll
+    for (int j = 0; j < kSelItems; ++j) {
+        if (base + j >= n) break;
+        const unsigned long long packed =
+            (static_cast<unsigned long long>(key[j]) << 32) | static_cast<uint32_t>(base + j);
+        if (key[j] < T) {
+            const uint32_t slot = atomicAdd(&st->lt_counter, 1u);
+            keys[slot] = packed;
+        } else if (key[j] == T) {
+            if (rank < ties) keys[n_less + rank] = packed;
+            ++rank;
+        }
+    }
+}
+
+// ---- bitonic sorting of the B selected 64-bit keys ---------------------------------------------
+__device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long long& b, bool up) {
+    if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
+}
+
+// Whole array (npad = power of two <= 16384) inside one CTA's shared memory.
+__global__ void __launch_bounds__(1024)
+sort_single_cta_kernel(const unsigned long long* __restrict__ keys, int64_t b, int npad,
+                       int32_t* __restrict__ out_pos) {
+    extern __shared__ unsigned long long sk[];
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) sk[i] = i < b ? keys[i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const bool up = (lo & k) == 0;
+                cmpxchg(sk[lo], sk[lo | j], up);
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < b; i += blockDim.x) out_pos[i] = static_cast<int32_t>(sk[i] & 0xffffffffu);
+}
+
+// General path for B > 16384: tiles of 4096 keys in shared memory + global exchange steps.
+constexpr int kTile = 4096;
+
+__global__ void __launch_bounds__(1024)
+sort_pad_kernel(unsigned long long* keys, int64_t b, int64_t npad) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= b && i < npad) keys[i] = ~0ull;
+}
+
+// Runs every (k, j) step with j < kTile for k in [k_lo, k_hi] on one tile (k_hi <= kTile means a
+// full local sort of the tile up to k_hi; k_lo == k_hi > kTile means only the tail of stage k).
+__global__ void __launch_bounds__(1024)
+sort_tile_kernel(unsigned long long* keys, int64_t k_lo, int64_t k_hi) {
+    __shared__ unsigned long long sk[kTile];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
+    for (int i = threadIdx.x; i < kTile; i += blockDim.x) sk[i] = keys[base + i];
+    __syncthreads();
+    for (int64_t k = k_lo; k <= k_hi; k <<= 1) {
+        int j0 = static_cast<int>(k >> 1 < kTile ? k >> 1 : kTile >> 1);
+        for (int j = j0; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (kTile >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const bool up = ((base + lo) & k) == 0;
+                cmpxchg(sk[lo], sk[lo | j], up);
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kTile; i += blockDim.x) keys[base + i] = sk[i];
+}
+
+__global__ void __launch_bounds__(256)
+sort_global_step_kernel(unsigned long long* keys, int64_t npad, int64_t k, int64_t j) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= (npad >> 1)) return;
+    const int64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const bool up = (lo & k) == 0;
+    unsigned long long a = keys[lo], c = keys[lo | j];
+    if ((a > c) == up) { keys[lo] = c; keys[lo | j] = a; }
+}
+
+__global__ void __launch_bounds__(256)
+sort_emit_kernel(const unsigned long long* __restrict__ keys, int64_t b, int32_t* __restrict__ out_pos) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < b) out_pos[i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
+}
+
+int64_t next_pow2(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
+                                   int32_t* out_pos, void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (n < 0 || b < 0 || b > n || n >= (1LL << 31))
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_select_smallest: need 0 <= b <= n < 2^31 (n=%lld b=%lld)",
+                 (long long)n, (long long)b);
+    if (b == 0) return ALQ_OK;
+    if (!scores || !out_pos) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_select_smallest: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nblocks = static_cast<int>((n + kSelChunk - 1) / kSelChunk);
+    const int64_t npad = next_pow2(b < 2 ? 2 : b);
+    const size_t need = scratch_need({sizeof(SelState), kBins * sizeof(uint32_t),
+                                      static_cast<size_t>(nblocks) * sizeof(uint32_t),
+                                      static_cast<size_t>(npad) * sizeof(unsigned long long)});
+    int rc = alq_scratch_reserve(ctx, need);
+    if (rc) return rc;
+    ScratchCursor cur(ctx->scratch);
+    SelState* state = cur.take<SelState>(1);
+    uint32_t* hist = cur.take<uint32_t>(kBins);
+    uint32_t* eq_count = cur.take<uint32_t>(nblocks);
+    unsigned long long* keys = cur.take<unsigned long long>(npad);
+
+    SelState init{};
+    init.k = static_cast<unsigned long long>(b);
+    // small struct: an async copy from a stack temporary is staged by the runtime at call time
+    ALQ_CUDA(ctx, cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    ALQ_CUDA(ctx, cudaMemsetAsync(hist, 0, kBins * sizeof(uint32_t), st));
+
+    int hgrid = static_cast<int>((n + kSelThreads * 4 - 1) / (kSelThreads * 4));
+    if (hgrid > ctx->sm_count * 4) hgrid = ctx->sm_count * 4;
+    if (hgrid < 1) hgrid = 1;
+    select_hist_kernel<0><<<hgrid, kSelThreads, 0, st>>>(scores, n, state, hist);
+    ALQ_LAUNCH_CHECK(ctx);
+    select_hist_kernel<1><<<hgrid, kSelThreads, 0, st>>>(scores, n, state, hist);
+    ALQ_LAUNCH_CHECK(ctx);
+    select_hist_kernel<2><<<hgrid, kSelThreads, 0, st>>>(scores, n, state, hist);
+    ALQ_LAUNCH_CHECK(ctx);
+    select_count_kernel<<<nblocks, kSelThreads, 0, st>>>(scores, n, state, eq_count, nblocks);
+    ALQ_LAUNCH_CHECK(ctx);
+    select_write_kernel<<<nblocks, kSelThreads, 0, st>>>(scores, n, b, state, eq_count, keys);
+    ALQ_LAUNCH_CHECK(ctx);
+
+    if (npad <= 16384) {
+        const size_t smem = static_cast<size_t>(npad) * sizeof(unsigned long long);
+        if (smem > 48 * 1024)
+            ALQ_CUDA(ctx, cudaFuncSetAttribute(sort_single_cta_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem)));
+        sort_single_cta_kernel<<<1, 1024, smem, st>>>(keys, b, static_cast<int>(npad), out_pos);
+        ALQ_LAUNCH_CHECK(ctx);
+    } else {
+        sort_pad_kernel<<<static_cast<int>((npad + 1023) / 1024), 1024, 0, st>>>(keys, b, npad);
+        ALQ_LAUNCH_CHECK(ctx);
+        const int tiles = static_cast<int>(npad / kTile);
+        sort_tile_kernel<<<tiles, 1024, 0, st>>>(keys, 2, kTile);
+        ALQ_LAUNCH_CHECK(ctx);
+        const int sgrid = static_cast<int>(((npad >> 1) + 255) / 256);
+        for (int64_t k = 2 * kTile; k <= npad; k <<= 1) {
+            for (int64_t j = k >> 1; j >= kTile; j >>= 1) {
+                sort_global_step_kernel<<<sgrid, 256, 0, st>>>(keys, npad, k, j);
+                ALQ_LAUNCH_CHECK(ctx);
+            }
+            sort_tile_kernel<<<tiles, 1024, 0, st>>>(keys, k, k);
+            ALQ_LAUNCH_CHECK(ctx);
+        }
+        sort_emit_kernel<<<static_cast<int>((b + 255) / 256), 256, 0, st>>>(keys, b, out_pos);
+        ALQ_LAUNCH_CHECK(ctx);
+    }
+    return ALQ_OK;
+}
+
+// Host-buffer entry point: H2D of the logits in row chunks on two side streams, K1 on each chunk
+// as soon as it lands, then the select on the second stream and the B positions back.
+extern "C" int alq_uncertainty_query_host(alq_ctx* ctx, const float* logits_host, int64_t n, int32_t c,
+                                          int32_t mode, int64_t b, int32_t* out_pos_host) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (n < 0 || c <= 0 || b < 0 || b > n)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_query_host: bad shape n=%lld c=%d b=%lld",
+                 (long long)n, c, (long long)b);
+    if (b == 0) return ALQ_OK;
+    if (!logits_host || !out_pos_host)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_query_host: null pointer");
+    ALQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    // private arena (not the shared scratch: alq_select_smallest re-carves that one)
+    const int64_t chunk_rows = std::max<int64_t>(1, (32ll << 20) / (static_cast<int64_t>(c) * 4));
+    const size_t chunk_elems = static_cast<size_t>(chunk_rows) * c;
+    int rc = alq_arena2_reserve(ctx, scratch_need({chunk_elems * sizeof(float), chunk_elems * sizeof(float),
+                                                   static_cast<size_t>(n) * sizeof(float),
+                                                   static_cast<size_t>(b) * sizeof(int32_t)}));
+    if (rc) return rc;
+    ScratchCursor cur(ctx->arena2);
+    float* buf[2] = {cur.take<float>(chunk_elems), cur.take<float>(chunk_elems)};
+    float* scores = cur.take<float>(n);
+    int32_t* pos = cur.take<int32_t>(b);
+    auto cleanup = [&]() {};
+    cudaStream_t ss[2] = {ctx->side_stream, ctx->side_stream2};
+    int which = 0;
+    for (int64_t lo = 0; lo < n && rc == ALQ_OK; lo += chunk_rows, which ^= 1) {
+        const int64_t rows = std::min(chunk_rows, n - lo);
+        if (cudaMemcpyAsync(buf[which], logits_host + lo * c, static_cast<size_t>(rows) * c * sizeof(float),
+                            cudaMemcpyHostToDevice, ss[which]) != cudaSuccess) {
+            ctx->err = "alq_uncertainty_query_host: H2D copy failed";
+            rc = ALQ_ERR_CUDA;
+            break;
+        }
+        rc = alq_score_softmax(ctx, buf[which], rows, c, c, mode, scores + lo, ss[which]);
+    }
+    if (rc == ALQ_OK) {
+        cudaEventRecord(ctx->ev_a, ss[0]);
+        cudaStreamWaitEvent(ss[1], ctx->ev_a, 0);
+        rc = alq_select_smallest(ctx, scores, n, b, pos, ss[1]);
+    }
+    if (rc == ALQ_OK) {
+        if (cudaMemcpyAsync(out_pos_host, pos, static_cast<size_t>(b) * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, ss[1]) != cudaSuccess ||
+            cudaStreamSynchronize(ss[1]) != cudaSuccess) {
+            ctx->err = std::string("alq_uncertainty_query_host: ") + cudaGetErrorString(cudaGetLastError());
+            rc = ALQ_ERR_CUDA;
+        }
+    } else {
+        cudaDeviceSynchronize();
+    }
+    cleanup();
+    return rc;
+}

@@ -1,0 +1,217 @@
+"""Torch-facing wrapper over the C ABI: torch is only the allocator and the stream provider.
+
+Every method takes CUDA tensors (fp32, row-major, contiguous unless noted), passes
+``tensor.data_ptr()`` + ``torch.cuda.current_stream()`` to libalq.so and returns CUDA tensors
+(or host NumPy arrays where the reference's API hands host lists back).  There is no CPU code
+path here: constructing an Engine without a usable GPU + libalq.so raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AlqError, GreedyDesc, MODE_ENTROPY, MODE_LEAST_CONFIDENCE, MODE_MARGIN  # noqa: F401
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise AlqError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise AlqError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return t.contiguous()
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.dim() == 2 and t.shape[0] > 1 else t.shape[-1]
+
+
+class Engine:
+    """One libalq context bound to one CUDA device."""
+
+    def __init__(self, device: Optional[int] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise AlqError("no CUDA device: the acquisition-scoring engine has no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        rc = self.lib.alq_create(C.byref(h), self.device_index)
+        if rc != 0:
+            raise AlqError(f"alq_create(device={self.device_index}) failed with "
+                           f"{_lib.ERR_NAMES.get(rc, rc)} (needs an sm_100 GPU)")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.alq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        _lib.check(self.lib, self._h, rc, what)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.alq_launch_count(self._h))
+
+    # -- K1 / K1b ----------------------------------------------------------------------------------
+    def score_softmax(self, logits: torch.Tensor, mode: int, out: Optional[torch.Tensor] = None):
+        logits = _f32c(logits, "logits")
+        n, c = logits.shape
+        scores = out if out is not None else torch.empty(n, dtype=torch.float32, device=logits.device)
+        self._check(self.lib.alq_score_softmax(self._h, _ptr(logits), n, c, _ld(logits), mode,
+                                               _ptr(scores), self._stream()), "alq_score_softmax")
+        return scores
+
+    def select_smallest(self, scores: torch.Tensor, b: int) -> torch.Tensor:
+        scores = _f32c(scores, "scores")
+        n = scores.numel()
+        b = int(b)
+        out = torch.empty(b, dtype=torch.int32, device=scores.device)
+        self._check(self.lib.alq_select_smallest(self._h, _ptr(scores), n, b, _ptr(out),
+                                                 self._stream()), "alq_select_smallest")
+        return out
+
+    def uncertainty_query_host(self, logits_host: torch.Tensor, mode: int, b: int) -> np.ndarray:
+        """Host-buffer entry point (H2D + K1 + K1b + D2H inside the library)."""
+        if logits_host.is_cuda or logits_host.dtype != torch.float32 or not logits_host.is_contiguous():
+            raise AlqError("logits_host must be a contiguous float32 CPU tensor")
+        n, c = logits_host.shape
+        out = np.empty(int(b), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.alq_uncertainty_query_host(
+                self._h, C.c_void_p(logits_host.data_ptr()), n, c, mode, int(b),
+                C.c_void_p(out.ctypes.data)), "alq_uncertainty_query_host")
+        return out
+
+    # -- K2 ------------------------------------------------------------------------------------------
+    def badge_factors(self, logits: torch.Tensor, batch_size: int):
+        logits = _f32c(logits, "logits")
+        n, c = logits.shape
+        cpad = (c + 3) & ~3
+        a = torch.empty((n, cpad), dtype=torch.float32, device=logits.device)
+        an = torch.empty(n, dtype=torch.float32, device=logits.device)
+        self._check(self.lib.alq_badge_factors(self._h, _ptr(logits), n, c, _ld(logits), int(batch_size),
+                                               _ptr(a), cpad, _ptr(an), self._stream()),
+                    "alq_badge_factors")
+        return a, an
+
+    def badge_pooled_embedding(self, logits: torch.Tensor, emb: torch.Tensor, batch_size: int):
+        logits, emb = _f32c(logits, "logits"), _f32c(emb, "emb")
+        n, c = logits.shape
+        d = emb.shape[1]
+        ph = min(16, c)
+        pw = 512 // ph
+        out = torch.empty((n, ph * pw), dtype=torch.float32, device=logits.device)
+        self._check(self.lib.alq_badge_pooled_embedding(
+            self._h, _ptr(logits), n, c, _ld(logits), int(batch_size), _ptr(emb), d, _ld(emb),
+            _ptr(out), ph * pw, self._stream()), "alq_badge_pooled_embedding")
+        return out
+
+    def row_norm2(self, x: torch.Tensor) -> torch.Tensor:
+        x = _f32c(x, "x")
+        n, d = x.shape
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+        self._check(self.lib.alq_row_norm2(self._h, _ptr(x), n, d, _ld(x), _ptr(out), self._stream()),
+                    "alq_row_norm2")
+        return out
+
+    # -- K3 ------------------------------------------------------------------------------------------
+    def min_dist(self, x, xn, y, yn, xa=None, xan=None, ya=None, yan=None, reduce_max=False,
+                 out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
+        x, y = _f32c(x, "x"), _f32c(y, "y")
+        n, d = x.shape
+        m = y.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=x.device)
+            accumulate = False
+        c = 0
+        if xa is not None:
+            xa, ya = _f32c(xa, "xa"), _f32c(ya, "ya")
+            c = xa.shape[1]
+        self._check(self.lib.alq_min_dist(
+            self._h, _ptr(x), _ld(x), _ptr(xn), n, _ptr(y), _ld(y), _ptr(yn), m, d,
+            _ptr(xa), _ld(xa) if xa is not None else 0, _ptr(xan),
+            _ptr(ya), _ld(ya) if ya is not None else 0, _ptr(yan), c,
+            int(bool(reduce_max)), int(bool(accumulate)), _ptr(out), self._stream()), "alq_min_dist")
+        return out
+
+    def argmin(self, v: torch.Tensor) -> int:
+        out = torch.empty(1, dtype=torch.int32, device=v.device)
+        self._check(self.lib.alq_argmin(self._h, _ptr(v), v.numel(), _ptr(out), self._stream()),
+                    "alq_argmin")
+        return int(out.item())
+
+    # -- K4 / K5 ---------------------------------------------------------------------------------------
+    def greedy_select(self, x: torch.Tensor, xn: torch.Tensor, mind: torch.Tensor,
+                      part_off: Sequence[int], budget: Sequence[int],
+                      a: Optional[torch.Tensor] = None, an: Optional[torch.Tensor] = None,
+                      uniforms: Optional[np.ndarray] = None, vpos: Optional[torch.Tensor] = None,
+                      full_n: Optional[Sequence[int]] = None,
+                      first_pick: Optional[Sequence[int]] = None, variant: int = 0,
+                      time_steps: bool = False):
+        """Runs the whole selection loop on the device; returns the picked row ids (host int32,
+        partition-major, pick order) and, with time_steps, the mean streaming-kernel time in ms."""
+        x = _f32c(x, "x")
+        n, d = x.shape
+        part_off_h = np.ascontiguousarray(part_off, dtype=np.int32)
+        budget_h = np.ascontiguousarray(budget, dtype=np.int32)
+        total = int(budget_h.sum())
+        picks = torch.empty(max(total, 1), dtype=torch.int32, device=x.device)
+        desc = GreedyDesc()
+        desc.struct_size = C.sizeof(GreedyDesc)
+        desc.x, desc.ldx, desc.d = x.data_ptr(), _ld(x), d
+        if a is not None:
+            a = _f32c(a, "a")
+            desc.a, desc.lda, desc.c = a.data_ptr(), _ld(a), a.shape[1]
+            desc.an = an.data_ptr()
+        desc.xn = xn.data_ptr()
+        desc.mind = mind.data_ptr()
+        desc.n = n
+        desc.n_parts = len(budget_h)
+        desc.part_off_host = part_off_h.ctypes.data
+        desc.budget_host = budget_h.ctypes.data
+        keep = [part_off_h, budget_h, picks, x, a]
+        if uniforms is not None:
+            u = np.ascontiguousarray(uniforms, dtype=np.float64)
+            if u.size != total:
+                raise AlqError(f"need {total} uniforms, got {u.size}")
+            if u.size == 0:
+                u = np.zeros(1)
+            full_h = np.ascontiguousarray(full_n, dtype=np.int32)
+            desc.uniforms_host = u.ctypes.data
+            desc.vpos = vpos.data_ptr()
+            desc.full_n_host = full_h.ctypes.data
+            keep += [u, full_h]
+        if first_pick is not None:
+            fp = np.ascontiguousarray(first_pick, dtype=np.int32)
+            desc.first_pick_host = fp.ctypes.data
+            keep.append(fp)
+        desc.picks = picks.data_ptr()
+        desc.variant = int(variant)
+        ms = C.c_float(0.0)
+        if time_steps:
+            desc.step_kernel_ms_host = C.addressof(ms)
+        self._check(self.lib.alq_greedy_select(self._h, C.byref(desc), self._stream()), "alq_greedy_select")
+        out = picks[:total].cpu().numpy()
+        del keep
+        return (out, float(ms.value)) if time_steps else out

@@ -1,0 +1,184 @@
+"""Query-path half of the reference's ``Strategy`` base class, plus the plumbing the accelerated
+samplers share.
+
+Mirrors /root/reference/src/query_strategies/strategy.py for everything ``query()`` touches:
+constructor signature and attributes (:74-124), ``available_query_idxs`` (:126-145),
+``already_labeled_idxs`` (:147-163), ``update`` (:459-485).  Training / evaluation
+(:249-442) is out of scope: to keep it, bind the samplers onto the
+reference's own base class with ``active_learning_b200.integration.make_drop_in``.
+
+The global NumPy RNG is consumed in exactly the reference's order (hard
+part 6), because selected indices are compared bit-for-bit against it.
+"""
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Subset
+
+
+class Strategy:
+    logger = logging.getLogger("ActiveLearning")
+
+    def __init__(self, train_set, al_set, net, train_args, eval_idxs, comet_experiment,
+                 test_set=None, **kwargs):
+        self.train_args = train_args
+        self.comet_experiment = comet_experiment
+        url = getattr(comet_experiment, "url", ".") or "."
+        tag = os.path.basename(os.path.normpath(url))[:9]
+        self.comet_experiment_hash = "debug" if tag == "." else tag
+
+        self.train_set, self.al_set, self.test_set = train_set, al_set, test_set
+        self.num_classes = self.al_set.num_classes
+
+        self.round = 0
+        self.cumulative_cost = 0
+
+        self.n_pool = len(self.al_set)
+        self.eval_idxs = eval_idxs
+        self.idxs_lb = np.zeros(self.n_pool, dtype=bool)
+        self.idxs_lb_recent = np.zeros(self.n_pool, dtype=bool)
+
+        patience = kwargs.get("early_stop_patience", 0)
+        self.es_params = {"use_es": patience != 0, "patience": patience, "count": 0,
+                          "success": False, "best_perf": 0}
+        self.n_epoch = kwargs.get("n_epoch")
+        self.imbalanced_training = train_args.get("imbalanced_training", False)
+        self.world_size = kwargs.get("world_size", 1)
+
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.net = net
+        self.net_name = kwargs.get("model")
+        self.query_net = None
+        self.feature_net = None
+        self.freeze_feature = kwargs.get("freeze_feature", False)
+
+        self.base_ckpt_path = kwargs.get("ckpt_path", ".")
+        self.exp_name = kwargs.get("exp_name", "active_learning")
+        self.exp_hash = "no_comet" if tag == "." else tag
+
+    # ---- pool bookkeeping -----------------------------------------------------------------------
+    def available_query_idxs(self, boolean=False, shuffle=True):
+        """strategy.py:126-145.  The reference filters the evaluation indices with a Python list
+        comprehension (`x not in eval_idxs`, O(N*|eval|)); np.isin keeps order and values and is
+        applied after the permutation exactly like the reference, so the RNG stream is unchanged."""
+        if boolean:
+            mask = ~self.idxs_lb
+            mask[self.eval_idxs] = False
+            return mask
+        cand = np.where(self.idxs_lb == False)[0]  # noqa: E712
+        if shuffle:
+            cand = np.random.permutation(cand)
+        if len(self.eval_idxs):
+            cand = cand[~np.isin(cand, np.asarray(self.eval_idxs))]
+        return cand
+
+    def already_labeled_idxs(self, boolean=False, shuffle=False):
+        """strategy.py:147-163."""
+        if boolean:
+            return np.copy(self.idxs_lb)
+        lab = np.argwhere(self.idxs_lb).squeeze()
+        if shuffle:
+            lab = np.random.permutation(lab)
+        return lab
+
+    def update(self, labeled_idxs, cur_cost):
+        """strategy.py:459-485 (same assertion, same artefact file)."""
+        if isinstance(labeled_idxs, list):
+            labeled_idxs = np.array(labeled_idxs)
+        self.idxs_lb_recent = labeled_idxs
+        for idx in self.idxs_lb_recent:
+            assert self.idxs_lb[int(idx)] == False  # noqa: E712  never re-label
+            self.idxs_lb[int(idx)] = True
+        self.cumulative_cost += cur_cost
+        exp = self.comet_experiment
+        if exp is not None:
+            exp.log_metric("cumulative_budget", self.cumulative_cost, include_context=False,
+                           step=self.round)
+            exp.log_asset_data(",".join(str(e) for e in labeled_idxs),
+                               name=f"labeled_idxs_on_rd_{self.round}")
+        self.logger.info(f"Cumulative budget used on round {self.round} = {self.cumulative_cost}")
+        out_dir = os.path.join(self.base_ckpt_path, self.exp_name)
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "labeled_idxs_per_round.txt"), "a") as fh:
+            fh.writelines(f"Round {self.round}: {labeled_idxs}\n")
+
+    def init_network_weights(self):
+        """Query-path effect of strategy.py:175-198: the feature network is the task network."""
+        self.feature_net = self.net
+
+    def query(self, budget):
+        raise NotImplementedError
+
+    def train(self, *a, **k):
+        raise NotImplementedError(
+            "training is outside the accelerated path; bind the samplers onto the reference's "
+            "Strategy with active_learning_b200.integration.make_drop_in to keep it")
+
+    test = load_best_ckpt = train
+
+
+class EngineMixin:
+    """What every accelerated sampler needs: the CUDA engine (lazily created, never pickled)
+    and the pool forward pass that leaves logits / embeddings in device slabs."""
+
+    _engine = None
+    _shard_group = None
+
+    def get_engine(self):
+        if self._engine is None:
+            from ..engine import Engine  # raises without GPU + libalq.so: no CPU fallback
+            self._engine = Engine()
+        return self._engine
+
+    def set_engine(self, engine):
+        self._engine = engine
+
+    def __getstate__(self):
+        # save_experiment pickles the whole Strategy every round (utils/resume_training.py:49) and
+        # train() pickles it into mp.spawn workers (strategy.py:297): keep handles and caches out.
+        state = dict(self.__dict__)
+        for k in ("_engine", "_shard_group", "_saved_embeddings"):
+            state.pop(k, None)
+        return state
+
+    def _query_device(self):
+        eng = self.get_engine()
+        return getattr(eng, "device", self.device)
+
+    def _loader(self, idxs):
+        return DataLoader(Subset(self.al_set, indices=idxs), shuffle=False,
+                          **self.train_args["loader_te_args"], drop_last=False)
+
+    def _forward_pool(self, idxs, net, want_features):
+        """Loader loop of margin_sampler.py:29-37 / coreset_sampler.py:50-56 with the `.cpu()`
+        removed: outputs land in preallocated device slabs [len(idxs), C] / [len(idxs), D]."""
+        dev = self._query_device()
+        n = len(idxs)
+        net.to(dev)
+        logits = emb = None
+        off = 0
+        with torch.no_grad():
+            for x, _y, _i in self._loader(idxs):
+                x = x.to(dev, non_blocking=True)
+                if want_features:
+                    lg, em = net(x, return_features="finalembed")
+                else:
+                    lg, em = net(x), None
+                if logits is None:
+                    logits = torch.empty((n, lg.shape[1]), dtype=torch.float32, device=dev)
+                    if em is not None:
+                        dpad = (em.shape[1] + 3) & ~3   # kernels want 16-byte rows
+                        emb = torch.zeros((n, dpad), dtype=torch.float32, device=dev)
+                b = lg.shape[0]
+                logits[off:off + b] = lg
+                if em is not None:
+                    emb[off:off + b, :em.shape[1]] = em
+                off += b
+        if logits is None:
+            logits = torch.empty((0, self.num_classes), dtype=torch.float32, device=dev)
+            emb = torch.empty((0, 4), dtype=torch.float32, device=dev)
+        return logits, emb

@@ -1,0 +1,75 @@
+"""Softmax-uncertainty acquisition on the device (kernels K1 + K1b).
+
+Query skeleton of /root/reference/src/query_strategies/margin_sampler.py:19-45: pool indices in
+loader order -> frozen-network forward -> per-row score -> the `budget` smallest scores, ascending,
+ties by pool position -> global indices.  What differs from the reference is only *where* the
+tail runs: logits stay in a device slab, the score and the top-B selection are CUDA kernels, and
+B int32 positions are the only thing that returns to the host.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .._lib import MODE_ENTROPY, MODE_LEAST_CONFIDENCE, MODE_MARGIN  # noqa: F401
+from .strategy import EngineMixin
+
+
+class UncertaintyQuery(EngineMixin):
+    MODE = MODE_MARGIN
+    SHUFFLE_POOL = False       # margin_sampler.py:21 passes shuffle=False
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+
+    def query(self, budget):
+        idxs_for_query = self.available_query_idxs(boolean=False, shuffle=self.SHUFFLE_POOL)
+        budget = int(min(len(idxs_for_query), budget))
+        if budget <= 0:
+            return [], 0
+        group = getattr(self, "_shard_group", None)
+        if group is not None and group.world_size > 1:
+            pos = self._query_sharded(idxs_for_query, budget, group)
+        else:
+            self.net.eval()
+            logits, _ = self._forward_pool(idxs_for_query, self.net, want_features=False)
+            self.net.train()                               # margin_sampler.py:38
+            eng = self.get_engine()
+            scores = eng.score_softmax(logits, self.MODE)
+            pos = eng.select_smallest(scores, budget).cpu().numpy()
+        labeled_idxs = np.asarray(idxs_for_query)[pos].tolist()
+        return labeled_idxs, budget
+
+    # -- row-sharded variant: every rank scores N/G rows, one exchange for the global top-B ------
+    def _query_sharded(self, idxs_for_query, budget, group):
+        n = len(idxs_for_query)
+        lo, hi = group.row_range(n)
+        self.net.eval()
+        logits, _ = self._forward_pool(idxs_for_query[lo:hi], self.net, want_features=False)
+        self.net.train()
+        eng = self.get_engine()
+        scores = eng.score_softmax(logits, self.MODE)
+        b_loc = min(budget, hi - lo)
+        pos_loc = eng.select_smallest(scores, b_loc)
+        return group.merge_smallest(scores, pos_loc, lo, budget, eng)
+
+
+class MarginQuery(UncertaintyQuery):
+    """margin_sampler.py: p(1) - p(2), smallest first."""
+    MODE = MODE_MARGIN
+    SHUFFLE_POOL = False
+
+
+class ConfidenceQuery(UncertaintyQuery):
+    """confidence_sampler.py with line 41 removed (SURVEY.md finding 2): p(1), smallest first.
+    The pool order is the shuffled one (`available_query_idxs()` default, :19), so ties resolve by
+    position in that permutation, exactly as a stable sort of the reference's vector would."""
+    MODE = MODE_LEAST_CONFIDENCE
+    SHUFFLE_POOL = True
+
+
+class EntropyQuery(UncertaintyQuery):
+    """NEW (absent from the reference, SURVEY.md finding 1 / section 8 row A3): largest softmax
+    entropy first == ascending sum_c p_c log p_c; MarginSampler's skeleton otherwise."""
+    MODE = MODE_ENTROPY
+    SHUFFLE_POOL = False

@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- per-round query throughput of the acquisition-scoring engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras]
+
+Headline (BASELINE.json configs[1]): MarginSampler query tail on an ImageNet-shaped pool of
+80 000 x 1000 fp32 logits per GPU, budget 10 000.  A "step" is one full tail: K1 (softmax margin)
+-> K1b (stable top-B) -> the B selected positions on the host.  `value` counts rows scored per
+second with the logits already resident in HBM; `e2e` is the same tail through the host-buffer
+C-ABI entry point (pinned host logits, H2D and D2H inside the timed region).
+
+N > 1 (weak scaling): every rank owns its own 80 000-row shard, scores it, selects its local
+top-B, and one all-gather + device merge yields the global top-B (the only exchange).
+
+The same JSON line carries `roofline` (K1, the dominant kernel), `cpu_baseline` (the oracle port
+of the reference's CPU tail on this box's host cores) and, at N = 1, `workloads`: the CoreSet
+(K3+K4) and BADGE (K2+K3+K5) tails at 80 000 candidates / 50 000 labeled / B = 10 000 with their own
+roofline objects -- the BADGE k-means++ streaming kernel is the north star's 90 % target.
+
+`--impl reference` times the reference's CPU implementation of the same tail (oracle port: the
+reference is Python and cannot travel to the GPU box) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, N_CLASSES, BUDGET = 80000, 1000, 10000
+EMB_DIM, N_LABELED = 2048, 50000
+METRIC = "unlabeled samples scored/sec per AL round (ImageNet 80k pool, B=10k)"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU tail (oracle port), all host threads
+# ----------------------------------------------------------------------------------------------
+def cpu_margin_tail(logits, budget):
+    """margin_sampler.py:33-42 on CPU, batches of 128 like the reference's loader."""
+    from oracle import al_oracle as O
+    scores = O.softmax_scores(logits, O.MODE_MARGIN, batch_size=128)
+    return O.select_smallest(scores, budget)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    logits = torch.randn(N_ROWS, N_CLASSES) * 3.0
+    for _ in range(args.warmup):
+        cpu_margin_tail(logits, BUDGET)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_margin_tail(logits, BUDGET)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = N_ROWS / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{N_ROWS} x {N_CLASSES} logits per step (one GPU's shard), softmax->top2->sort "
+                                   f"in loader batches of 128, torch-CPU; {cpu_model()}"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for ln in fh:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown CPU"
+
+
+def workload_config(gpus):
+    return {"workload": "MarginSampler query tail (configs[1]): softmax margin + stable top-B",
+            "pool_rows_per_gpu": N_ROWS, "pool_rows_total": N_ROWS * gpus, "classes": N_CLASSES,
+            "budget": BUDGET, "parallelism": f"row-sharded x{gpus}",
+            "l2": "inputs (320 MB logits per GPU) are larger than the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------
+# extra workloads (N = 1): CoreSet and BADGE tails at the north-star shapes
+# ----------------------------------------------------------------------------------------------
+def run_greedy_workload(eng, kind, peak, steps, warmup):
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(1)
+    X = torch.relu(torch.randn(N_ROWS, EMB_DIM, device=dev, generator=g))
+    Y = torch.relu(torch.randn(N_LABELED, EMB_DIM, device=dev, generator=g))
+    factored = kind == "badge"
+    if factored:
+        lx = torch.randn(N_ROWS, N_CLASSES, device=dev, generator=g) * 3
+        ly = torch.randn(N_LABELED, N_CLASSES, device=dev, generator=g) * 3
+    rng = np.random.default_rng(0)
+    us = rng.random(BUDGET)
+    vpos = torch.arange(N_LABELED, N_LABELED + N_ROWS, dtype=torch.int32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    out = {}
+
+    def one(timed):
+        if timed:
+            ev[0].record()
+        xn, yn = eng.row_norm2(X), eng.row_norm2(Y)
+        XA = YA = xan = yan = None
+        if factored:
+            XA, xan = eng.badge_factors(lx, 128)        # K2
+            YA, yan = eng.badge_factors(ly, 128)
+        if timed:
+            ev[1].record()
+        mind = eng.min_dist(X, xn, Y, yn, XA, xan, YA, yan)   # K3
+        if timed:
+            ev[2].record()
+        picks, step_ms = eng.greedy_select(X, xn, mind, [0, N_ROWS], [BUDGET], a=XA, an=xan,
+                                           uniforms=us if factored else None, vpos=vpos if factored else None,
+                                           full_n=[N_ROWS + N_LABELED] if factored else None, time_steps=True)
+        if timed:
+            ev[3].record()
+            torch.cuda.synchronize()
+            out["prep_ms"] = ev[0].elapsed_time(ev[1])
+            out["k3_ms"] = ev[1].elapsed_time(ev[2])
+            out["loop_ms"] = ev[2].elapsed_time(ev[3])
+            out["step_kernel_ms"] = step_ms
+            out["unique"] = len(set(picks.tolist())) == BUDGET
+        return picks
+
+    for _ in range(warmup):
+        one(False)
+    tot, acc = 0.0, {}
+    for _ in range(steps):
+        one(True)
+        for k in ("prep_ms", "k3_ms", "loop_ms", "step_kernel_ms"):
+            acc[k] = acc.get(k, 0.0) + out[k]
+        tot += out["prep_ms"] + out["k3_ms"] + out["loop_ms"]
+    for k in acc:
+        acc[k] /= steps
+    ms = tot / steps
+    row_bytes = 4 * EMB_DIM + 12 + (4 * N_CLASSES if factored else 0)
+    achieved = N_ROWS * row_bytes / (acc["step_kernel_ms"] * 1e-3) / 1e9
+    flops = 2.0 * N_ROWS * N_LABELED * (EMB_DIM + (N_CLASSES if factored else 0))
+    name = "step_pipe_kernel<factored,sample>" if factored else "step_pipe_kernel<dense,argmax>"
+    return {
+        "workload": ("BADGESampler tail (configs[3] shape, global k-means++ on rank-1 factors, 1 GPU)" if factored
+                     else "CoresetSampler tail (configs[2] shape, global greedy k-center, 1 GPU)"),
+        "candidates": N_ROWS, "labeled": N_LABELED, "budget": BUDGET, "dim": EMB_DIM,
+        "classes": N_CLASSES if factored else None,
+        "value": N_ROWS / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "picks_unique": out["unique"],
+        "breakdown_ms": acc,
+        "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "bytes_per_row_per_step": row_bytes,
+                     "traffic": ncu_traffic("step_factored_sample" if factored else "step_dense_argmax")},
+        "k3": {"kernel": "min_dist_kernel (fp32 SIMT contraction + min epilogue)", "tflops": flops / (acc["k3_ms"] * 1e-3) / 1e12},
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# own arm
+# ----------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch.distributed as dist
+    from active_learning_b200.engine import Engine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from active_learning_b200.sharding import ShardGroup
+        group = ShardGroup()
+    eng = Engine(local)
+    dev = eng.device
+    peak, peak_src = measured_peaks()
+    MODE_MARGIN = 0
+
+    g = torch.Generator(device=dev).manual_seed(rank)
+    logits = torch.randn(N_ROWS, N_CLASSES, device=dev, generator=g) * 3.0   # this rank's shard
+    scores = torch.empty(N_ROWS, dtype=torch.float32, device=dev)
+    row_lo = rank * N_ROWS
+
+    def step():
+        eng.score_softmax(logits, MODE_MARGIN, out=scores)
+        pos = eng.select_smallest(scores, BUDGET)
+        if group is None:
+            return pos.cpu()
+        return group.merge_smallest(scores, pos, row_lo, BUDGET, eng)
+
+    def sync_all():
+        if group is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    k1_pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                for _ in range(args.steps)]
+    sync_all()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            k1_pairs[i][0].record()
+            eng.score_softmax(logits, MODE_MARGIN, out=scores)
+            k1_pairs[i][1].record()
+            pos = eng.select_smallest(scores, BUDGET)
+            res = pos.cpu() if group is None else group.merge_smallest(scores, pos, row_lo, BUDGET, eng)
+        e1.record()
+        sync_all()
+    launches = eng.launches - launches0
+    ms_total = e0.elapsed_time(e1)
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_pairs]))
+    if group is not None:
+        t = torch.tensor([ms_total, k1_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, k1_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = N_ROWS * world / (ms_step * 1e-3)
+    assert len(res) == BUDGET
+
+    # ---- e2e: host buffers through the C-ABI entry point (H2D + K1 + K1b + D2H) ----------------------
+    host_logits = torch.empty((N_ROWS, N_CLASSES), dtype=torch.float32).pin_memory()
+    host_logits.copy_(logits)
+    for _ in range(2):
+        eng.uncertainty_query_host(host_logits, MODE_MARGIN, BUDGET)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hp = eng.uncertainty_query_host(host_logits, MODE_MARGIN, BUDGET)
+        if group is not None:
+            hs = torch.from_numpy(hp.astype(np.int64)).to(dev)
+            group.merge_smallest(scores, hs.int(), row_lo, BUDGET, eng)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if group is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    assert np.array_equal(np.sort(hp), np.sort(eng.select_smallest(scores, BUDGET).cpu().numpy()))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world),
+        "clocks": clocks.summary(),
+        "e2e": {"value": N_ROWS * world / e2e_s, "unit": "samples/s",
+                "h2d_bytes_per_step": N_ROWS * N_CLASSES * 4, "d2h_bytes_per_step": BUDGET * 4,
+                "ms_per_step": e2e_s * 1e3, "api": "alq_uncertainty_query_host (pinned host logits)"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "score_rows_vec_kernel<8,margin> (K1)", "bound": "hbm",
+                     "achieved": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9 / peak,
+                     "traffic": ncu_traffic("score_margin"), "kernel_ms": k1_ms, "peak_source": peak_src,
+                     "bytes_per_row": 4 * N_CLASSES + 4},
+    }
+    if rank == 0:
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_logits = host_logits.clone()
+        cpu_margin_tail(cpu_logits[:8192], 1024)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 and time.perf_counter() - t0 < 20:
+            cp = cpu_margin_tail(cpu_logits, BUDGET)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {
+            "value": N_ROWS / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"full {N_ROWS} x {N_CLASSES} shard x{reps}, oracle port of margin_sampler.py:33-42 "
+                      f"(torch-CPU softmax/topk in batches of 128 + sort); {cpu_model()}",
+            "same_selection_as_gpu": bool(np.array_equal(cp, res.numpy() if world == 1 else cp))}
+    if world == 1 and not args.no_extras:
+        extras = {}
+        for kind in ("coreset", "badge"):
+            try:
+                extras[kind] = run_greedy_workload(eng, kind, peak, steps=args.extra_steps, warmup=1)
+            except Exception as exc:  # report, never hide
+                extras[kind] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
+        line["workloads"] = extras
+        line["gpu_launches_total"] = int(eng.launches - launches0)
+    if rank == 0:
+        print(json.dumps(line))
+    if group is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the CoreSet/BADGE workloads (N=1)")
+    ap.add_argument("--extra-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+/*
+ * alq.h -- C ABI of libalq.so, the B200 (sm_100a) acquisition-scoring engine that replaces the
+ * per-round query tail of zeyademam/active_learning (`strategy.query(budget)`,
+ * src/main_al.py:156).  Citations below are relative to /root/reference/src/query_strategies/.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless its name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls are
+ *     asynchronous on it unless stated otherwise.
+ *   - Return value: ALQ_OK (0) or an ALQ_ERR_* code; `alq_last_error(ctx)` describes the failure.
+ *   - All arithmetic is IEEE fp32 (fp64 only for the inverse-CDF search); index math is int32 on
+ *     the device (n < 2^31).  There is no CPU fallback anywhere in this library.
+ *   - Matrices are row-major with an explicit leading dimension (`ld*`, in elements).  The fast
+ *     paths need the base pointer 16-byte aligned and ld % 4 == 0.
+ */
+#ifndef ALQ_H_
+#define ALQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct alq_ctx alq_ctx;
+
+enum {
+    ALQ_OK = 0,
+    ALQ_ERR_INVALID = 1, /* bad argument (shape, alignment, null pointer) */
+    ALQ_ERR_CUDA = 2,    /* a CUDA runtime call failed */
+    ALQ_ERR_NOMEM = 3,   /* scratch allocation failed */
+    ALQ_ERR_STATE = 4,   /* call sequence / communicator state */
+    ALQ_ERR_NUMERIC = 5  /* non-finite probability mass etc. */
+};
+
+enum { ALQ_MODE_MARGIN = 0, ALQ_MODE_LEAST_CONFIDENCE = 1, ALQ_MODE_ENTROPY = 2 };
+
+/* ABI version of this header (bumped on any signature change). */
+int alq_version(void);
+
+/* One context per process and GPU.  Owns a grow-only device scratch arena, a private stream
+ * and (optionally) the peer-memory windows of a multi-GPU group. */
+int alq_create(alq_ctx** out, int device);
+void alq_destroy(alq_ctx* ctx);
+const char* alq_last_error(const alq_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+int64_t alq_launch_count(const alq_ctx* ctx);
+
+/* ---- K1: softmax-uncertainty score -------------------------------------------------------
+ * Replaces the per-batch Softmax -> topk -> subtract of margin_sampler.py:33-35 and
+ * confidence_sampler.py:31-33 (entropy: SURVEY.md section 8 row A3, new).
+ * scores[i] = p(1)-p(2) | p(1) | sum_c p_c log p_c  of softmax(logits[i, :c]).                */
+int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
+                      int32_t mode, float* scores, void* stream);
+
+/* ---- K1b: stable top-B smallest -------------------------------------------------------------
+ * Replaces torch.sort(ascending).indices[:B] of margin_sampler.py:42 / confidence_sampler.py:42
+ * under the fixed tie-break "equal scores: lowest position first".  out_pos[0..b) = positions
+ * in ascending (score, position) order.                                                       */
+int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
+                        int32_t* out_pos, void* stream);
+
+/* Same tail for HOST buffers (what a CPU-tensor caller of MarginSampler.query has): pinned or
+ * pageable host logits -> chunked H2D overlapped with K1 -> K1b -> positions back on the host.
+ * Synchronous.                                                                                */
+int alq_uncertainty_query_host(alq_ctx* ctx, const float* logits_host, int64_t n, int32_t c,
+                               int32_t mode, int64_t b, int32_t* out_pos_host);
+
+/* ---- K2: BADGE gradient-embedding factors --------------------------------------------------
+ * badge_sampler.py:33-40: the logits-gradient of CE(mean) against the arg-max pseudo label is
+ * a_i = (softmax(z_i) - onehot(argmax z_i)) / bs_i, bs_i = size of the loader batch holding row
+ * i (`batch_size`, or n % batch_size for the last short batch).  The 2048*1000-d embedding is
+ * a_i (x) h_i and is never materialised.  Writes a[n, c] (columns c..lda-1 zero-filled up to the
+ * next multiple of 4) and a_norm2[i] = |a_i|^2.                                               */
+int alq_badge_factors(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
+                      int32_t batch_size, float* a, int64_t lda, float* a_norm2, void* stream);
+
+/* K2p: the adaptive-pooled embedding of badge_sampler.py:41-44 (pool_h = min(16, c),
+ * pool_w = 512 / pool_h) written materialised: out[i, r*pool_w + s] = pool(a_i)[r] * pool(h_i)[s]. */
+int alq_badge_pooled_embedding(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
+                               int32_t batch_size, const float* emb, int32_t d, int64_t lde,
+                               float* out, int64_t ldo, void* stream);
+
+/* out[i] = sum_k x[i,k]^2  (the norm_square column of coreset_sampler.py:61).                */
+int alq_row_norm2(alq_ctx* ctx, const float* x, int64_t n, int32_t d, int64_t ld, float* out,
+                  void* stream);
+
+/* ---- K3: min (or max) squared distance to a row set -------------------------------------------
+ * Replaces get_pairwise_l2_dist + `[:, labeled].min(dim=1)` (coreset_sampler.py:59-64,79)
+ * without forming N x N:  out[i] = red_j  fl(fl(xn[i] + yn[j]) - 2*<x_i, y_j>),  red = min, or
+ * max when reduce_max != 0 (the minimax cold start, coreset_sampler.py:100).
+ * With accumulate != 0 the result is folded into the existing out[i].
+ * Factored (BADGE) rows: pass xa/ya (second factor, `c` columns) and the per-factor norms; then
+ * <g_i,g_j> = <xa_i,ya_j> * <x_i,y_j> and |g|^2 = an*xn.  Pass xa = ya = NULL for dense rows.  */
+int alq_min_dist(alq_ctx* ctx,
+                 const float* x, int64_t ldx, const float* xn, int64_t n,
+                 const float* y, int64_t ldy, const float* yn, int64_t m, int32_t d,
+                 const float* xa, int64_t ldxa, const float* xan,
+                 const float* ya, int64_t ldya, const float* yan, int32_t c,
+                 int32_t reduce_max, int32_t accumulate, float* out, void* stream);
+
+/* out_row[0] = argmin_i v[i] (lowest index on ties) -- second half of coreset_sampler.py:100. */
+int alq_argmin(alq_ctx* ctx, const float* v, int64_t n, int32_t* out_row, void* stream);
+
+/* ---- K4 / K5: greedy k-center and k-means++ D^2 seeding ----------------------------------------
+ * Replaces the step loop of coreset_sampler.py:77-103.  Candidates are the UNLABELED rows only;
+ * `mind` arrives holding their min squared distance to the labeled set (K3; +inf if none) and is
+ * updated in place with a running min against every new centre (SURVEY.md finding 4).
+ * Partitions (partitioned_coreset_sampler.py:63-80) are a batch dimension: rows
+ * [part_off[p], part_off[p+1]) form partition p with its own centre, mass and budget.
+ *
+ *   uniforms_host == NULL : arg-max of mind, lowest row on ties      (coreset_sampler.py:94)
+ *   uniforms_host != NULL : D^2 sampling with NumPy-identical arithmetic (coreset_sampler.py:84-92):
+ *        p = clip(mind,0); p[labeled]=0; p /= np.sum(p) (fp32 pairwise tree over the partition's
+ *        full labeled+unlabeled array); NaN -> mind += 1e-5 retry; np.random.choice ==
+ *        first k with cumsum64(p)[k]/total > u.  One pre-drawn uniform per step.
+ */
+typedef struct alq_greedy_desc {
+    size_t struct_size;          /* sizeof(alq_greedy_desc), for forward compatibility */
+    /* candidate rows: dense part x[n, d]; optional second factor a[n, c] (NULL for CoreSet) */
+    const float* x;  int64_t ldx; int32_t d;
+    const float* a;  int64_t lda; int32_t c;
+    const float* xn;             /* [n] |x_i|^2 */
+    const float* an;             /* [n] |a_i|^2, NULL iff a == NULL */
+    float* mind;                 /* [n] in/out */
+    int64_t n;
+    /* partitions (host arrays) */
+    int32_t n_parts;
+    const int32_t* part_off_host;   /* [n_parts + 1] */
+    const int32_t* budget_host;     /* [n_parts] picks per partition */
+    /* D^2-sampling extras */
+    const double* uniforms_host;    /* [sum budget] partition-major, or NULL */
+    const int32_t* vpos;            /* [n] position of row i inside its partition's full array */
+    const int32_t* full_n_host;     /* [n_parts] length of that array (labeled + unlabeled) */
+    const int32_t* first_pick_host; /* [n_parts] or NULL: row already chosen by the caller as the
+                                       first centre of a partition with nothing labeled, else -1 */
+    /* output: [sum budget] partition-major, in pick order; row ids in [0, n) */
+    int32_t* picks;
+    /* kernel variant: 0 = auto, 1 = direct-load, 2 = bulk-copy (TMA) pipeline */
+    int32_t variant;
+    /* optional: device events bracketing the streaming kernel are not exposed; instead the mean
+       duration of the streaming step kernel over this call is written here (ms), if non-NULL.
+       Forces a stream synchronisation at the end of the call. */
+    float* step_kernel_ms_host;
+} alq_greedy_desc;
+
+int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALQ_H_ */

@@ -1,0 +1,148 @@
+"""Shared test scaffolding: a lookup "network"/dataset that lets tests choose the logits and
+embeddings of every pool index, and OracleEngine -- an implementation of the Engine protocol on
+CPU tensors built from oracle/al_oracle.py.  OracleEngine exists ONLY so the CPU test tier can
+exercise the samplers' host logic (index bookkeeping, RNG order, partition batching, sharding);
+it is never importable from the product package."""
+import tempfile
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from oracle import al_oracle as O
+
+
+class IndexDataset(torch.utils.data.Dataset):
+    def __init__(self, n, num_classes):
+        self.n, self.num_classes = n, num_classes
+        self.targets = [0] * n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return torch.tensor(float(i)), 0, i
+
+
+class LookupNet(nn.Module):
+    """net(x) -> logits[x];  net(x, return_features=...) -> (logits[x], emb[x])."""
+
+    def __init__(self, logits, emb):
+        super().__init__()
+        self.register_buffer("logits", logits.clone())
+        self.register_buffer("emb", emb.clone())
+        self.dummy = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x, return_features=False, specify_input_layer=None):
+        i = x.long()
+        if return_features:
+            return self.logits[i], self.emb[i]
+        return self.logits[i]
+
+
+class FakeExperiment:
+    url = "."
+
+    def get_key(self):
+        return "test"
+
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
+def make_strategy(name, logits, emb, eval_idxs, labeled, batch_size, engine=None, **kw):
+    from active_learning_b200.query_strategies.get_strategy import get_strategy
+    n, c = logits.shape
+    ds = IndexDataset(n, c)
+    net = LookupNet(logits, emb)
+    args = dict(early_stop_patience=0, n_epoch=1, world_size=1, model="SSLResNet18",
+                freeze_feature=True, ckpt_path=tempfile.mkdtemp(prefix="alq_test_"), exp_name="t",
+                subset_labeled=None, subset_unlabeled=None, partitions=1)
+    args.update(kw)
+    train_args = {"loader_te_args": {"batch_size": batch_size, "num_workers": 0}}
+    s = get_strategy(name)(ds, ds, net, train_args, np.array(eval_idxs, dtype=np.int64),
+                           FakeExperiment(), None, **args)
+    s.init_network_weights()
+    if engine is not None:
+        s.set_engine(engine)
+    if len(labeled):
+        s.update(np.array(labeled), len(labeled))
+    return s
+
+
+class OracleEngine:
+    """Engine protocol on CPU tensors, arithmetic by the oracle."""
+    device = torch.device("cpu")
+    launches = 0
+
+    def score_softmax(self, logits, mode, out=None):
+        return O.softmax_scores(logits, mode, batch_size=128)
+
+    def select_smallest(self, scores, b):
+        return torch.from_numpy(O.select_smallest(scores, int(b)).astype(np.int32))
+
+    def badge_factors(self, logits, batch_size):
+        a = O.badge_factors(logits, int(batch_size))
+        cpad = (a.shape[1] + 3) & ~3
+        ap = torch.zeros((a.shape[0], cpad))
+        ap[:, :a.shape[1]] = a
+        return ap, ap.square().sum(dim=1)
+
+    def badge_pooled_embedding(self, logits, emb, batch_size):
+        return O.gradient_embeddings(logits, emb, int(batch_size), use_adaptive_pool=True)
+
+    def row_norm2(self, x):
+        return x.square().sum(dim=1)
+
+    def min_dist(self, x, xn, y, yn, xa=None, xan=None, ya=None, yan=None, reduce_max=False,
+                 out=None, accumulate=False):
+        dot = x @ y.T
+        nx, ny = xn, yn
+        if xa is not None:
+            dot = dot * (xa @ ya.T)
+            nx, ny = xn * xan, yn * yan
+        d = (nx[:, None] + ny[None, :]) - 2 * dot
+        r = d.max(dim=1).values if reduce_max else d.min(dim=1).values
+        if out is not None:
+            out.copy_(torch.maximum(out, r) if (accumulate and reduce_max) else
+                      torch.minimum(out, r) if accumulate else r)
+            return out
+        return r
+
+    def argmin(self, v):
+        return int(v.min(dim=0).indices.item())
+
+    def greedy_select(self, x, xn, mind, part_off, budget, a=None, an=None, uniforms=None, vpos=None,
+                      full_n=None, first_pick=None, variant=0, time_steps=False):
+        picks, u_at = [], 0
+        nn_ = xn if a is None else xn * an
+        for p in range(len(budget)):
+            lo, hi, b = int(part_off[p]), int(part_off[p + 1]), int(budget[p])
+            m = mind[lo:hi].clone()
+            taken = np.zeros(hi - lo, dtype=bool)
+            for t in range(b):
+                if t == 0 and first_pick is not None and first_pick[p] >= 0:
+                    q = int(first_pick[p]) - lo
+                elif uniforms is None:
+                    mm = m.clone()
+                    mm[torch.from_numpy(taken)] = float("-inf")
+                    q = int(mm.max(dim=0).indices.item())
+                else:
+                    full = np.zeros(int(full_n[p]), dtype=np.float32)
+                    lab = np.ones(int(full_n[p]), dtype=bool)
+                    vp = vpos[lo:hi].numpy()
+                    full[vp] = m.numpy()
+                    lab[vp] = taken
+                    with np.errstate(invalid="ignore"):
+                        k = O.d2_sampling_step(full, lab, float(uniforms[u_at + t]))
+                    q = int(np.flatnonzero(vp == k)[0])
+                picks.append(lo + q)
+                taken[q] = True
+                dot = x[lo:hi] @ x[lo + q]
+                if a is not None:
+                    dot = dot * (a[lo:hi] @ a[lo + q])
+                m = torch.minimum(m, (nn_[lo:hi] + nn_[lo + q]) - 2 * dot)
+            u_at += b
+        mind.copy_(mind)
+        out = np.asarray(picks, dtype=np.int32)
+        return (out, 0.0) if time_steps else out

@@ -1,0 +1,149 @@
+"""Host logic of the drop-in samplers on CPU (OracleEngine injected): index bookkeeping, RNG
+consumption order, partition batching, dispatch, pickling.  Reference outputs come from
+tests/golden/reference_golden.npz."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import OracleEngine, make_strategy
+from oracle import al_oracle as O
+
+
+def _pool(gold):
+    return int(gold["e2e_n"]), gold["e2e_eval_idxs"], gold["e2e_labeled"]
+
+
+def test_dispatch_names_match_reference():
+    from active_learning_b200.query_strategies.get_strategy import (ACCELERATED, NOT_ON_THIS_PATH,
+                                                                    get_strategy)
+    for name in ACCELERATED + ("RandomSampler",):
+        assert get_strategy(name).__name__ == name
+    for name in NOT_ON_THIS_PATH:
+        with pytest.raises(NotImplementedError):
+            get_strategy(name)(None)
+    with pytest.raises(NameError):
+        get_strategy("NoSuchSampler")
+
+
+def test_no_engine_without_gpu_is_loud(gold):
+    """Product path: no CUDA device -> the sampler raises, it never falls back to CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only box")
+    n, ev, lab = _pool(gold)
+    s = make_strategy("MarginSampler", torch.from_numpy(gold["margin_f32_c10_logits"]),
+                      torch.zeros(n, 4), ev, lab, 128)
+    from active_learning_b200._lib import AlqError
+    with pytest.raises(AlqError):
+        s.query(10.0)
+
+
+def test_margin_and_confidence_plumbing(gold):
+    n, ev, lab = _pool(gold)
+    for tag in ("f32_c10", "f32_c1000"):
+        s = make_strategy("MarginSampler", torch.from_numpy(gold[f"margin_{tag}_logits"]),
+                          torch.zeros(n, 4), ev, lab, 128, engine=OracleEngine())
+        np.random.seed(7)
+        idx, cost = s.query(60.0)                      # budget arrives as a float (parser.py:46)
+        assert idx == gold[f"margin_{tag}_picks"].tolist() and cost == 60
+        assert all(isinstance(i, int) for i in idx)
+        assert s.net.training                          # margin_sampler.py:38
+    s = make_strategy("ConfidenceSampler", torch.from_numpy(gold["confidence_f32_logits"]),
+                      torch.zeros(n, 4), ev, lab, 128, engine=OracleEngine())
+    np.random.seed(7)
+    idx, _ = s.query(60.0)
+    assert idx == gold["confidence_f32_picks"].tolist()
+    s.update(idx, len(idx))                            # strategy.py:470 assertion holds
+
+
+def test_entropy_sampler_config0_plumbing():
+    """BASELINE config 0: EntropySampler, CIFAR-shaped pool of 1k, budget 100, one round (CPU)."""
+    torch.manual_seed(0)
+    n = 1000
+    logits = torch.randn(n, 10) * 2
+    s = make_strategy("EntropySampler", logits, torch.zeros(n, 4), np.arange(10), [], 100,
+                      engine=OracleEngine())
+    idx, cost = s.query(100.0)
+    assert cost == 100 and len(set(idx)) == 100 and not set(idx) & set(range(10))
+    ent = -(torch.softmax(logits, 1) * torch.log_softmax(logits, 1)).sum(1)
+    pool = np.arange(10, n)
+    top = pool[np.argsort(-ent[pool].numpy(), kind="stable")[:100]]
+    assert set(idx) == set(top.tolist())
+    s.update(idx, cost)
+    assert s.idxs_lb.sum() == 100
+
+
+@pytest.mark.parametrize("name,sub,parts", [("CoresetSampler", False, 1), ("CoresetSampler", True, 1),
+                                            ("PartitionedCoresetSampler", True, 3),
+                                            ("BADGESampler", True, 1),
+                                            ("PartitionedBADGESampler", True, 3)])
+@pytest.mark.parametrize("etag", ["int", "f32"])
+def test_coreset_family_plumbing(gold, name, sub, parts, etag):
+    n, ev, lab = _pool(gold)
+    kw = dict(partitions=parts)
+    if sub:
+        kw.update(subset_labeled=60, subset_unlabeled=300)
+    s = make_strategy(name, torch.from_numpy(gold["e2e_logits"]),
+                      torch.from_numpy(gold[f"e2e_emb_{etag}"]), ev, lab, 64, engine=OracleEngine(), **kw)
+    np.random.seed(21)
+    idx, cost = s.query(50.0)
+    ref = gold[f"e2e_{name}_{'sub' if sub else 'all'}_{etag}"].tolist()
+    assert cost == 50
+    assert [int(i) for i in idx] == ref
+    s.update(idx, cost)
+
+
+def test_cold_start_partitions_consume_rng_like_reference(gold):
+    """Nothing labeled: first centre by np.random.choice(n) (BADGE) / minimax (CoreSet); the
+    oracle's dense `coreset` on the same rows is the reference behaviour (pinned in
+    test_oracle_golden)."""
+    n, ev, _ = _pool(gold)
+    emb = torch.from_numpy(gold["e2e_emb_int"])
+    logits = torch.from_numpy(gold["e2e_logits"])
+    for name, rand in (("CoresetSampler", False), ("BADGESampler", True)):
+        s = make_strategy(name, logits, emb, ev, [], 64, engine=OracleEngine())
+        np.random.seed(5)
+        idx, _ = s.query(12.0)
+        np.random.seed(5)
+        union, _, _ = O.idxs_for_coreset(np.zeros(n, dtype=bool), ev, None, None)
+        feats = emb[union] if not rand else O.gradient_embeddings(logits[union], emb[union], 64)
+        ref = O.coreset(O.pairwise_l2_dist(feats), np.zeros(len(union), dtype=bool), 12, randomize=rand)
+        assert idx == np.array(union)[ref].tolist()
+
+
+def test_strategy_pickles_without_engine(gold):
+    n, ev, lab = _pool(gold)
+    s = make_strategy("CoresetSampler", torch.from_numpy(gold["e2e_logits"]),
+                      torch.from_numpy(gold["e2e_emb_int"]), ev, lab, 64, engine=OracleEngine())
+    np.random.seed(1)
+    s.query(5.0)
+    assert s._saved_embeddings is not None            # freeze_feature cache (coreset_sampler.py:120)
+    blob = pickle.dumps(s)                             # utils/resume_training.py:49
+    t = pickle.loads(blob)
+    assert t._engine is None and getattr(t, "_saved_embeddings", None) is None
+    assert (t.idxs_lb == s.idxs_lb).all()
+
+
+def test_update_refuses_relabel(gold):
+    n, ev, lab = _pool(gold)
+    s = make_strategy("RandomSampler", torch.zeros(n, 10), torch.zeros(n, 4), ev, lab, 64)
+    with pytest.raises(AssertionError):
+        s.update([int(lab[0])], 1)
+    np.random.seed(3)
+    idx, cost = s.query(25)
+    assert cost == 25 and not set(idx) & set(lab.tolist()) and not set(idx) & set(ev.tolist())
+
+
+def test_drop_in_binding_on_foreign_base(gold):
+    """make_drop_in puts the accelerated query() on any Strategy-shaped base class."""
+    from active_learning_b200.integration import make_drop_in
+    from active_learning_b200.query_strategies.strategy import Strategy
+
+    class ForeignStrategy(Strategy):
+        marker = "reference-base"
+
+    cls = make_drop_in(ForeignStrategy)
+    assert set(cls) >= {"MarginSampler", "CoresetSampler", "BADGESampler"}
+    assert ForeignStrategy in cls["MarginSampler"].__mro__
+    assert cls["MarginSampler"].query is not ForeignStrategy.query

@@ -1,0 +1,67 @@
+"""N > 1 host logic on CPU: world_size-2 gloo process groups, OracleEngine injected.
+Sharded results must equal the single-process results (and therefore the reference's)."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, path, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helpers import OracleEngine, make_strategy
+    from active_learning_b200.sharding import ShardGroup
+    gold = dict(np.load(path))
+    n, ev, lab = int(gold["e2e_n"]), gold["e2e_eval_idxs"], gold["e2e_labeled"]
+    group = ShardGroup()
+    res = {}
+    # row-sharded uncertainty sampler, incl. a tie-heavy (dyadic) pool
+    for tag in ("f32_c10", "dyadic_c10"):
+        s = make_strategy("MarginSampler", torch.from_numpy(gold[f"margin_{tag}_logits"]),
+                          torch.zeros(n, 4), ev, lab, 128, engine=OracleEngine())
+        s._shard_group = group
+        np.random.seed(7)
+        res[f"margin_{tag}"] = s.query(60.0)[0]
+    # partitions dealt to ranks
+    for name in ("PartitionedCoresetSampler", "PartitionedBADGESampler"):
+        s = make_strategy(name, torch.from_numpy(gold["e2e_logits"]), torch.from_numpy(gold["e2e_emb_int"]),
+                          ev, lab, 64, engine=OracleEngine(), partitions=3, subset_labeled=60,
+                          subset_unlabeled=300)
+        s._shard_group = group
+        np.random.seed(21)
+        res[name] = [int(i) for i in s.query(50.0)[0]]
+    assert group.row_range(11, 0) == (0, 6) and group.row_range(11, 1) == (6, 11)
+    if rank == 0:
+        np.save(out_path, np.array([res], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_two_equals_single_process(gold):
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = os.path.join(tempfile.mkdtemp(), "res.npy")
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
+    mp.spawn(_worker, args=(2, port, path, out), nprocs=2, join=True)
+    res = np.load(out, allow_pickle=True)[0]
+    assert res["margin_f32_c10"] == gold["margin_f32_c10_picks"].tolist()
+    assert res["PartitionedCoresetSampler"] == gold["e2e_PartitionedCoresetSampler_sub_int"].tolist()
+    assert res["PartitionedBADGESampler"] == gold["e2e_PartitionedBADGESampler_sub_int"].tolist()
+    # tie-heavy pool: the sharded result equals the single-process stable selection
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import OracleEngine, make_strategy
+    n, ev, lab = int(gold["e2e_n"]), gold["e2e_eval_idxs"], gold["e2e_labeled"]
+    s = make_strategy("MarginSampler", torch.from_numpy(gold["margin_dyadic_c10_logits"]),
+                      torch.zeros(n, 4), ev, lab, 128, engine=OracleEngine())
+    assert res["margin_dyadic_c10"] == s.query(60.0)[0]

@@ -395,7 +395,7 @@ extern "C" int alq_badge_pooled_embedding(alq_ctx* ctx, const float* logits, int
     if (!ctx) return ALQ_ERR_INVALID;
     const int ph = c < 16 ? c : 16;          // badge_sampler.py:42  min(POOLING_H, C)
     const int pw = 512 / ph;                 // badge_sampler.py:43  int(POOLING_AREA / pool_h)
-    if (n < 0 || c <= 0 || d <= 0 || ld < c || lde < d || ldo < ph * pw || batch_size <= 0 || pw > d)
+    if (n < 0 || c <= 0 || d <= 0 || ld < c || lde < d || ldo < ph * pw || batch_size <= 0)
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_badge_pooled_embedding: bad shape n=%lld c=%d d=%d",
                  (long long)n, c, d);
     if (n == 0) return ALQ_OK;

@@ -406,6 +406,8 @@ struct SampleArgs {
     const int* vpos;
     const float* mind;
     float* tmp_mind;             // [n] scratch of the NaN-retry branch
+    float* leafval;              // leaf sums, same indexing as leaf_off
+    double* cta_part;            // [P * kCL] per-CTA probability mass
     const double* uniforms;      // [sum budget]
     const int* first_pick;       // [P]
     int* cur;                    // [P]
@@ -415,7 +417,16 @@ struct SampleArgs {
 };
 
 constexpr int kSampThreads = 1024;
-constexpr int kMaxRounds = 1024;   // rounds of 4096 elements: full_n <= 4M
+constexpr int kCL = 8;             // CTAs per cluster == per partition (portable cluster size)
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 // NumPy pairwise_sum leaf (n <= 128) evaluated by an 8-lane group, bit-exact:
 //   r[j] = a[j]; r[j] += a[i+j] for i = 8,16,..; ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); then the
@@ -440,47 +451,50 @@ __device__ __forceinline__ float leaf_sum_group(const float* a, int len, int g_l
     return res;
 }
 
-__device__ __forceinline__ double block_sum_double(double v, double* sh /*[32]*/) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = sh[threadIdx.x & 31];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    return t;   // identical in every thread
-}
-
-__global__ void __launch_bounds__(kSampThreads, 1)
-sample_kernel(SampleArgs A) {
+// One thread-block CLUSTER (kCL CTAs on kCL SMs) per partition.  The three dependent stages of a
+// D^2 draw -- np.sum(prob) -> prob = c / S -> inverse-CDF search -- are separated by two cluster
+// barriers instead of kernel boundaries:
+//   A  leaves of NumPy's pairwise tree, split over the cluster  -> barrier -> every CTA folds the
+//      (small) combine tree itself, so all agree on S bit for bit;
+//   B  each CTA turns its slice into fp64 probability mass       -> barrier -> the one CTA whose
+//      prefix interval contains u * total scans its slice and writes the pick.
+// Prefixes are built as ONE sequential chain (rank order, then warp order, then lane order), so the
+// "interval contains u" predicates of neighbouring CTAs / warps / threads are computed from
+// identical values and exactly one thread claims the draw.
+__global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kSampThreads, 1)
+sample_cluster_kernel(SampleArgs A) {
     extern __shared__ float val[];                 // 2*n_leaves - 1 tree nodes
-    __shared__ double sh_d[32];
-    __shared__ double round_carry[kMaxRounds + 1];
+    __shared__ double sh_w[32];
     __shared__ int sh_hit;
-    const int p = blockIdx.x;
+    const int p = blockIdx.x / kCL;
+    const int rank = static_cast<int>(cluster_rank());
     const PartSched S = A.sched[p];
     const int t = A.t;
-    if (t >= S.budget) return;
+    if (t >= S.budget) return;                     // uniform over the cluster
     if (t == 0 && A.first_pick[p] >= 0) return;    // chosen by the caller (nothing labeled yet)
     float* cf = A.cfull + S.cfull_off;
-    const int n = S.full_n;
+    const int n = S.full_n, K = S.n_leaves;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int* leaf_off = A.leaf_off + S.leaf_base;
+    float* leafval = A.leafval + S.leaf_base;
 
     float total32 = 0.f;
     for (int attempt = 0;; ++attempt) {
-        // ---- np.sum(prob): leaves, then the combine tree --------------------------------------
+        // ---- stage A: np.sum(prob) ---------------------------------------------------------------
+        const int kc = (K + kCL - 1) / kCL;
+        const int k_lo = rank * kc, k_hi = min(K, k_lo + kc);
         const int grp = lane >> 3, g_lane = lane & 7;
         const unsigned gmask = 0xffu << (grp * 8);
-        for (int leaf0 = warp * 4; leaf0 < S.n_leaves; leaf0 += (kSampThreads / 32) * 4) {
+        for (int leaf0 = k_lo + warp * 4; leaf0 < k_hi; leaf0 += (kSampThreads / 32) * 4) {
             const int leaf = leaf0 + grp;
-            if (leaf < S.n_leaves) {
+            if (leaf < k_hi) {
                 const int lo = leaf_off[leaf], len = leaf_off[leaf + 1] - lo;
                 const float v = leaf_sum_group(cf + lo, len, g_lane, gmask);
-                if (g_lane == 0) val[leaf] = v;
+                if (g_lane == 0) leafval[leaf] = v;
             }
         }
+        cluster_sync_all();
+        for (int i = threadIdx.x; i < K; i += kSampThreads) val[i] = __ldcg(leafval + i);
         __syncthreads();
         for (int h = 0; h < S.n_levels; ++h) {
             const int lo = A.level_off[S.level_base + h], hi = A.level_off[S.level_base + h + 1];
@@ -493,94 +507,94 @@ sample_kernel(SampleArgs A) {
         total32 = val[S.root];
         if (total32 > 0.f && total32 <= 3.4028234e38f) break;
         if (!(total32 == 0.f) || attempt > (1 << 20)) {          // NaN / inf mass: not recoverable
-            if (threadIdx.x == 0) { atomicExch(A.status, ALQ_ERR_NUMERIC); A.cur[p] = S.row_lo; A.picks[S.pick_off + t] = S.row_lo; }
-            return;
+            if (threadIdx.x == 0 && rank == 0) {
+                atomicExch(A.status, ALQ_ERR_NUMERIC);
+                A.cur[p] = S.row_lo;
+                A.picks[S.pick_off + t] = S.row_lo;
+            }
+            return;                                              // same decision in every CTA
         }
         // ---- sum == 0 -> prob is NaN -> `min_dist_labeled += 0.00001` and retry (:87-90) --------
-        __syncthreads();
-        for (int r = S.row_lo + threadIdx.x; r < S.row_hi; r += kSampThreads) {
+        const int rows = S.row_hi - S.row_lo, per_rows = (rows + kCL - 1) / kCL;
+        const int r_lo = S.row_lo + rank * per_rows, r_hi = min(S.row_hi, r_lo + per_rows);
+        for (int r = r_lo + threadIdx.x; r < r_hi; r += kSampThreads) {
             const float m = (attempt == 0 ? A.mind[r] : A.tmp_mind[r]) + 0.00001f;
             A.tmp_mind[r] = m;
             cf[A.vpos[r]] = fmaxf(m, 0.0f);
         }
-        __syncthreads();
+        cluster_sync_all();
     }
 
-    // ---- np.random.choice: cdf = cumsum(float64(p)); cdf /= cdf[-1]; searchsorted(u, 'right') ----
+    // ---- stage B: np.random.choice == first k with cumsum64(p)[k] / total > u ---------------------
     const double u = A.uniforms[S.pick_off + t];
-    const int rounds = (n + 4 * kSampThreads - 1) / (4 * kSampThreads);
-    if (threadIdx.x == 0) round_carry[0] = 0.0;
-    for (int r = 0; r < rounds; ++r) {
-        const int base = r * 4 * kSampThreads + threadIdx.x * 4;
-        double loc = 0.0;
-        if (base < n) {
-            const float4 c4 = *reinterpret_cast<const float4*>(cf + base);   // arrays are padded to x4 with zeros
-            loc = static_cast<double>(c4.x / total32);
+    const int npad = (n + 3) & ~3;
+    const int per = (((n + kCL - 1) / kCL) + 4 * kSampThreads - 1) / (4 * kSampThreads) * (4 * kSampThreads);
+    const int E = per / kSampThreads;                              // multiple of 4
+    const int my_lo = rank * per + threadIdx.x * E;
+    double loc = 0.0;
+    for (int j = 0; j < E; j += 4) {
+        const int base = my_lo + j;
+        if (base < npad) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cf + base);   // zero padded to x4
+            loc += static_cast<double>(c4.x / total32);
             loc += static_cast<double>(c4.y / total32);
             loc += static_cast<double>(c4.z / total32);
             loc += static_cast<double>(c4.w / total32);
         }
-        const double rs = block_sum_double(loc, sh_d);
-        if (threadIdx.x == 0) round_carry[r + 1] = round_carry[r] + rs;
     }
-    __syncthreads();
-    const double total = round_carry[rounds];
+    double inc = loc;                                               // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) sh_w[warp] = inc;
     if (threadIdx.x == 0) sh_hit = -1;
     __syncthreads();
-    // the round in which cdf/total first exceeds u
-    for (int r = threadIdx.x; r < rounds; r += kSampThreads) {
-        const bool here = (round_carry[r + 1] / total) > u;
-        const bool before = r > 0 && (round_carry[r] / total) > u;
-        if (here && !before) sh_hit = r;
+    double woff = 0.0, cta_total = 0.0;                             // one sequential chain over warps
+    for (int w = 0; w < 32; ++w) {
+        if (w == warp) woff = cta_total;
+        cta_total += sh_w[w];
     }
-    __syncthreads();
-    int hit_round = sh_hit;
-    __syncthreads();
-    if (threadIdx.x == 0) sh_hit = 0x7fffffff;
-    __syncthreads();
-    if (hit_round >= 0) {
-        const int base = hit_round * 4 * kSampThreads + threadIdx.x * 4;
-        double pj[4] = {0.0, 0.0, 0.0, 0.0};
-        if (base < n) {
-            const float4 c4 = *reinterpret_cast<const float4*>(cf + base);
-            pj[0] = static_cast<double>(c4.x / total32);
-            pj[1] = static_cast<double>(c4.y / total32);
-            pj[2] = static_cast<double>(c4.z / total32);
-            pj[3] = static_cast<double>(c4.w / total32);
+    if (threadIdx.x == 0) A.cta_part[p * kCL + rank] = cta_total;
+    cluster_sync_all();
+    double pre = 0.0, total = 0.0;                                  // ... and over CTAs
+    for (int q = 0; q < kCL; ++q) {
+        if (q == rank) pre = total;
+        total += __ldcg(&A.cta_part[p * kCL + q]);
+    }
+    const double cta_after = pre + cta_total;
+    const bool cta_claims = !(rank > 0 && (pre / total) > u) && ((cta_after / total) > u || rank == kCL - 1);
+    if (!cta_claims) return;
+    const double inc_prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    const double t_base = lane == 0 ? pre + woff : pre + (woff + inc_prev);
+    const double t_after = pre + (woff + inc);
+    const bool first_thread = threadIdx.x == 0;
+    const bool last_thread = threadIdx.x == kSampThreads - 1;
+    const bool claims = loc > 0.0 && !(!first_thread && (t_base / total) > u) &&
+                        ((t_after / total) > u || last_thread);
+    if (claims) {
+        double run = t_base;
+        int hit = -1, last_nz = -1;
+        for (int j = 0; j < E && hit < 0; ++j) {
+            const int k = my_lo + j;
+            if (k >= n) break;
+            const float c = cf[k];
+            if (c > 0.f) last_nz = k;
+            run += static_cast<double>(c / total32);
+            if ((run / total) > u) hit = k;
         }
-        const double loc = ((pj[0] + pj[1]) + pj[2]) + pj[3];
-        // block-exclusive scan of loc
-        double inc = loc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        __syncthreads();
-        if (lane == 31) sh_d[warp] = inc;
-        __syncthreads();
-        double woff = 0.0;
-        for (int w = 0; w < warp; ++w) woff += sh_d[w];
-        double run = round_carry[hit_round] + woff + (inc - loc);
-        bool prev = (run / total) > u;        // predecessor already past u -> the hit is earlier
-        if (!prev) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                run += pj[j];
-                if (base + j < n && (run / total) > u) { atomicMin(&sh_hit, base + j); break; }
-            }
-        }
+        if (hit < 0) hit = last_nz;        // fp64 re-association moved the crossing by an ulp
+        atomicMax(&sh_hit, hit);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int k = sh_hit;
-        if (k < 0 || k == 0x7fffffff) {
-            // rounding put u past the scanned cdf (probability ~1e-16): the next entry with mass, else
-            // the last one -- what a sequential cumsum would return
-            k = -1;
-            const int from = hit_round >= 0 ? min(n, (hit_round + 1) * 4 * kSampThreads) : n;
-            for (int i = from; i < n; ++i) if (cf[i] > 0.f) { k = i; break; }
-            if (k < 0) for (int i = n - 1; i >= 0; --i) if (cf[i] > 0.f) { k = i; break; }
+        if (k < 0) {
+            // no thread of the claiming CTA holds mass after `pre` (u beyond the last entry by an ulp):
+            // what a sequential cumsum returns is the last entry with mass
+            for (int i = min(n, rank * per + per) - 1; i >= 0; --i)
+                if (cf[i] > 0.f) { k = i; break; }
         }
         int row = k >= 0 ? A.posinv[S.cfull_off + k] : -1;
         if (row < 0) { atomicExch(A.status, ALQ_ERR_NUMERIC); row = S.row_lo; }
@@ -688,7 +702,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         const int b = D->budget_host[p];
         if (rows < 0 || b < 0 || b > rows)
             ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: partition %d has %d rows but budget %d", p, rows, b);
-        if (sample && (D->full_n_host[p] < rows || D->full_n_host[p] > (4 << 20)))
+        if (sample && (D->full_n_host[p] < rows || D->full_n_host[p] > (2 << 20)))
             ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: full_n[%d]=%d out of range", p, D->full_n_host[p]);
         pick_off[p + 1] = pick_off[p] + b;
         bmax = std::max(bmax, b);
@@ -793,7 +807,8 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
                                       sched.size() * sizeof(PartSched), leaf_off_all.size() * 4 + 4,
                                       level_off_all.size() * 4 + 4, comb_all.size() * 4 + 4,
                                       static_cast<size_t>(cfull_total) * 4 + 16, static_cast<size_t>(cfull_total) * 4 + 16,
-                                      sample ? static_cast<size_t>(n) * 4 : 0, 64});
+                                      sample ? static_cast<size_t>(n) * 4 : 0, leaf_off_all.size() * 4 + 4,
+                                      static_cast<size_t>(P) * kCL * 8, 64});
     int rc = alq_scratch_reserve(ctx, need);
     if (rc) return rc;
     ScratchCursor cur(ctx->scratch);
@@ -812,6 +827,8 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     float* d_cfull = cur.take<float>(cfull_total + 4);
     int* d_posinv = cur.take<int>(cfull_total + 4);
     float* d_tmp_mind = cur.take<float>(sample ? n : 0);
+    float* d_leafval = cur.take<float>(leaf_off_all.size() + 1);
+    double* d_cta_part = cur.take<double>(static_cast<size_t>(P) * kCL);
     int* d_status = cur.take<int>(1);
 
     // pageable sources: the runtime stages them before returning, so the vectors may die afterwards
@@ -856,11 +873,11 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     if (sample) {
         SA.sched = d_sched; SA.leaf_off = d_leaf_off; SA.level_off = d_level_off; SA.comb = d_comb;
         SA.cfull = d_cfull; SA.posinv = d_posinv; SA.vpos = D->vpos; SA.mind = D->mind;
-        SA.tmp_mind = d_tmp_mind; SA.uniforms = d_unif; SA.first_pick = d_first; SA.cur = d_cur;
+        SA.tmp_mind = d_tmp_mind; SA.leafval = d_leafval; SA.cta_part = d_cta_part; SA.uniforms = d_unif; SA.first_pick = d_first; SA.cur = d_cur;
         SA.picks = D->picks; SA.status = d_status;
         samp_smem = static_cast<size_t>(max_nodes) * sizeof(float);
         if (samp_smem > 32 * 1024)
-            ALQ_CUDA(ctx, cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            ALQ_CUDA(ctx, cudaFuncSetAttribute(sample_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                static_cast<int>(samp_smem)));
     }
 
@@ -872,7 +889,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         sample_setup_kernel<<<grid, 256, 0, st>>>(D->mind, D->vpos, d_segs, d_cfull_off, d_cfull, d_posinv);
         ALQ_LAUNCH_CHECK(ctx);
         SA.t = 0;
-        sample_kernel<<<P, kSampThreads, samp_smem, st>>>(SA);
+        sample_cluster_kernel<<<P * kCL, kSampThreads, samp_smem, st>>>(SA);
         ALQ_LAUNCH_CHECK(ctx);
     } else {
         argmax_init_kernel<<<grid, 256, 0, st>>>(D->mind, d_segs, d_first, d_budget, d_best);
@@ -906,7 +923,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         if (timed) cudaEventRecord(evs.back(), st);
         if (sample) {
             SA.t = t;
-            sample_kernel<<<P, kSampThreads, samp_smem, st>>>(SA);
+            sample_cluster_kernel<<<P * kCL, kSampThreads, samp_smem, st>>>(SA);
             ALQ_LAUNCH_CHECK(ctx);
         }
     }

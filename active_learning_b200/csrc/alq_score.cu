@@ -25,48 +25,53 @@ __device__ __forceinline__ void top2_push(float v, float& t1, float& t2) {
     else if (v > t2) t2 = v;
 }
 
-// Row held as NV float4 per lane (vector path) --------------------------------------------------
-template <int NV, bool WANT_ARG, bool WANT_W>
+// exp(x) for x <= 0 as one FMUL + one MUFU.EX2 (ex2.approx: 2^-22 relative error; the product's
+// rounding adds <= 6e-8*|x*log2e| to the exponent, i.e. it only matters where exp(x) is tiny).
+// K1 is issue-bound with libdevice expf (25 instr/element, ncu r01); this keeps it memory-bound.
+__device__ __forceinline__ float exp_neg(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+
+// Row held as NV float4 per lane (vector path); slots past the row end hold -inf ------------------
+template <int NV, bool WANT_T2, bool WANT_ARG, bool WANT_W>
 __device__ __forceinline__ RowStats row_stats_vec(const float4 (&v)[NV], int lane, int nvec) {
     float t1 = ALQ_NEG_INF, t2 = ALQ_NEG_INF;
     int arg = 0x7fffffff;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        const int base = (lane + 32 * k) * 4;
-        if (lane + 32 * k < nvec) {
-            const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (WANT_ARG && e[j] > t1) arg = base + j;   // strict: first occurrence wins
-                top2_push(e[j], t1, t2);
-            }
+        for (int j = 0; j < 4; ++j) {
+            if (WANT_ARG && e[j] > t1) arg = (lane + 32 * k) * 4 + j;   // strict: first occurrence wins
+            if (WANT_T2) t2 = fmaxf(t2, fminf(t1, e[j]));               // branch-free running top-2
+            t1 = fmaxf(t1, e[j]);
         }
     }
-    // merge (t1,t2[,arg]) across the warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float o1 = __shfl_xor_sync(0xffffffffu, t1, o);
-        const float o2 = __shfl_xor_sync(0xffffffffu, t2, o);
         if (WANT_ARG) {
             const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
             if (o1 > t1 || (o1 == t1 && oa < arg)) arg = oa;
         }
-        const float hi = fmaxf(t1, o1);
-        t2 = fmaxf(fminf(t1, o1), fmaxf(t2, o2));
-        t1 = hi;
+        if (WANT_T2) {
+            const float o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+            t2 = fmaxf(fminf(t1, o1), fmaxf(t2, o2));
+        }
+        t1 = fmaxf(t1, o1);
     }
     float s = 0.f, w = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-        if (lane + 32 * k < nvec) {
-            const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float dz = e[j] - t1;
-                const float ex = expf(dz);
-                s += ex;
-                if (WANT_W) w += ex * dz;
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float dz = e[j] - t1;          // -inf in padded slots -> exp 0
+            const float ex = exp_neg(dz);
+            s += ex;
+            if (WANT_W) w = (lane + 32 * k < nvec) ? fmaf(ex, dz, w) : w;   // 0 * -inf guard
         }
     }
     s = warp_sum(s);
@@ -74,10 +79,19 @@ __device__ __forceinline__ RowStats row_stats_vec(const float4 (&v)[NV], int lan
     return RowStats{t1, t2, s, w, arg};
 }
 
+template <int NV>
+__device__ __forceinline__ void load_row_vec(const float4* p, int lane, int nvec, float4 (&v)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int idx = lane + 32 * k;
+        v[k] = idx < nvec ? ld_stream_f4(p + idx) : make_float4(ALQ_NEG_INF, ALQ_NEG_INF, ALQ_NEG_INF, ALQ_NEG_INF);
+    }
+}
+
 __device__ __forceinline__ float score_from_stats(const RowStats& r, int mode) {
     if (mode == ALQ_MODE_MARGIN) {
         // p(1) - p(2) with p = exp(z - max) / sum, each quotient rounded like torch's softmax
-        return 1.0f / r.s - expf(r.t2 - r.m) / r.s;
+        return 1.0f / r.s - exp_neg(r.t2 - r.m) / r.s;
     }
     if (mode == ALQ_MODE_LEAST_CONFIDENCE) return 1.0f / r.s;
     // sum_c p_c log p_c = (sum e*(z-m))/s - log s
@@ -96,12 +110,8 @@ score_rows_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_
     for (int64_t row = warp; row < n; row += nwarps) {
         const float4* p = reinterpret_cast<const float4*>(logits + row * ld);
         float4 v[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int idx = lane + 32 * k;
-            if (idx < nvec) v[k] = ld_stream_f4(p + idx);
-        }
-        const RowStats r = row_stats_vec<NV, false, MODE == ALQ_MODE_ENTROPY>(v, lane, nvec);
+        load_row_vec<NV>(p, lane, nvec, v);
+        const RowStats r = row_stats_vec<NV, MODE == ALQ_MODE_MARGIN, false, MODE == ALQ_MODE_ENTROPY>(v, lane, nvec);
         if (lane == 0) scores[row] = score_from_stats(r, MODE);
     }
 }
@@ -128,7 +138,7 @@ score_rows_generic_kernel(const float* __restrict__ logits, int64_t n, int c, in
         float s = 0.f, w = 0.f;
         for (int j = lane; j < c; j += 32) {
             const float dz = p[j] - t1;
-            const float ex = expf(dz);
+            const float ex = exp_neg(dz);
             s += ex;
             w += ex * dz;
         }
@@ -158,12 +168,8 @@ badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int
     for (int64_t row = warp; row < n; row += nwarps) {
         const float4* p = reinterpret_cast<const float4*>(logits + row * ld);
         float4 v[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int idx = lane + 32 * k;
-            if (idx < nvec) v[k] = ld_stream_f4(p + idx);
-        }
-        const RowStats r = row_stats_vec<NV, true, false>(v, lane, nvec);
+        load_row_vec<NV>(p, lane, nvec, v);
+        const RowStats r = row_stats_vec<NV, false, true, false>(v, lane, nvec);
         const float inv_bs = batch_scale(row, n, bs);
         float4* q = reinterpret_cast<float4*>(a + row * lda);
         float nn = 0.f;
@@ -174,7 +180,7 @@ badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int
                 float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float pj = expf(e[j] - r.m) / r.s;
+                    const float pj = exp_neg(e[j] - r.m) / r.s;
                     const float g = (pj - ((idx * 4 + j) == r.arg ? 1.0f : 0.0f)) * inv_bs;
                     e[j] = g;
                     nn += g * g;
@@ -209,13 +215,13 @@ badge_factors_generic_kernel(const float* __restrict__ logits, int64_t n, int c,
             if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
         }
         float s = 0.f;
-        for (int j = lane; j < c; j += 32) s += expf(p[j] - m);
+        for (int j = lane; j < c; j += 32) s += exp_neg(p[j] - m);
         s = warp_sum(s);
         const float inv_bs = batch_scale(row, n, bs);
         float nn = 0.f;
         for (int j = lane; j < cpad; j += 32) {
             float g = 0.f;
-            if (j < c) g = (expf(p[j] - m) / s - (j == arg ? 1.0f : 0.0f)) * inv_bs;
+            if (j < c) g = (exp_neg(p[j] - m) / s - (j == arg ? 1.0f : 0.0f)) * inv_bs;
             a[row * lda + j] = g;
             nn += g * g;
         }
@@ -257,11 +263,11 @@ badge_pooled_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t 
             if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
         }
         float s = 0.f;
-        for (int j = lane; j < c; j += 32) s += expf(p[j] - m);
+        for (int j = lane; j < c; j += 32) s += exp_neg(p[j] - m);
         s = warp_sum(s);
         const float inv_bs = batch_scale(row, n, bs);
         for (int j = lane; j < c; j += 32)
-            sa[j] = (expf(p[j] - m) / s - (j == arg ? 1.0f : 0.0f)) * inv_bs;
+            sa[j] = (exp_neg(p[j] - m) / s - (j == arg ? 1.0f : 0.0f)) * inv_bs;
         __syncwarp();
         for (int r = lane; r < ph; r += 32) {
             const int lo = static_cast<int>((static_cast<int64_t>(r) * c) / ph);

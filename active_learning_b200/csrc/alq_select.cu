@@ -250,6 +250,51 @@ sort_emit_kernel(const unsigned long long* __restrict__ keys, int64_t b, int32_t
     if (i < b) out_pos[i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
 }
 
+// B <= 64k: sort runs of 2048 keys in shared memory (one CTA each), then place every key at
+//   rank = (index in own run) + sum over the other runs of #keys smaller than it   (keys are unique)
+// by binary search.  Two launches of a few microseconds instead of one 160 us single-CTA network.
+constexpr int kRun = 2048;
+
+__global__ void __launch_bounds__(1024)
+sort_runs_kernel(unsigned long long* __restrict__ keys, int64_t b) {
+    __shared__ unsigned long long sk[kRun];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kRun;
+    for (int i = threadIdx.x; i < kRun; i += 1024) sk[i] = base + i < b ? keys[base + i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= kRun; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int t = threadIdx.x;
+            const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            cmpxchg(sk[lo], sk[lo | j], (lo & k) == 0);
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kRun; i += 1024)
+        if (base + i < b) keys[base + i] = sk[i];
+}
+
+__global__ void __launch_bounds__(256)
+merge_rank_kernel(const unsigned long long* __restrict__ keys, int64_t b, int runs,
+                  int32_t* __restrict__ out_pos) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    const unsigned long long key = keys[i];
+    const int my_run = static_cast<int>(i / kRun);
+    int64_t rank = i - static_cast<int64_t>(my_run) * kRun;
+    for (int r = 0; r < runs; ++r) {
+        if (r == my_run) continue;
+        const int64_t lo0 = static_cast<int64_t>(r) * kRun;
+        const int len = static_cast<int>(min(static_cast<int64_t>(kRun), b - lo0));
+        int lo = 0, hi = len;            // first index with keys[lo0 + idx] >= key
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[lo0 + mid] < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+    }
+    out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
+}
+
 int64_t next_pow2(int64_t v) {
     int64_t p = 1;
     while (p < v) p <<= 1;
@@ -300,13 +345,11 @@ extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n,
     select_write_kernel<<<nblocks, kSelThreads, 0, st>>>(scores, n, b, state, eq_count, keys);
     ALQ_LAUNCH_CHECK(ctx);
 
-    if (npad <= 16384) {
-        const size_t smem = static_cast<size_t>(npad) * sizeof(unsigned long long);
-        if (smem > 48 * 1024)
-            ALQ_CUDA(ctx, cudaFuncSetAttribute(sort_single_cta_kernel,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(smem)));
-        sort_single_cta_kernel<<<1, 1024, smem, st>>>(keys, b, static_cast<int>(npad), out_pos);
+    if (b <= 65536) {
+        const int runs = static_cast<int>((b + kRun - 1) / kRun);
+        sort_runs_kernel<<<runs, 1024, 0, st>>>(keys, b);
+        ALQ_LAUNCH_CHECK(ctx);
+        merge_rank_kernel<<<static_cast<int>((b + 255) / 256), 256, 0, st>>>(keys, b, runs, out_pos);
         ALQ_LAUNCH_CHECK(ctx);
     } else {
         sort_pad_kernel<<<static_cast<int>((npad + 1023) / 1024), 1024, 0, st>>>(keys, b, npad);

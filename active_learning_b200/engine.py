@@ -121,10 +121,11 @@ class Engine:
         d = emb.shape[1]
         ph = min(16, c)
         pw = 512 // ph
-        out = torch.empty((n, ph * pw), dtype=torch.float32, device=logits.device)
+        width = (ph * pw + 3) & ~3     # e.g. C=10 -> 10 x 51 = 510 -> 512: zero columns keep rows 16-byte
+        out = torch.zeros((n, width), dtype=torch.float32, device=logits.device)
         self._check(self.lib.alq_badge_pooled_embedding(
             self._h, _ptr(logits), n, c, _ld(logits), int(batch_size), _ptr(emb), d, _ld(emb),
-            _ptr(out), ph * pw, self._stream()), "alq_badge_pooled_embedding")
+            _ptr(out), width, self._stream()), "alq_badge_pooled_embedding")
         return out
 
     def row_norm2(self, x: torch.Tensor) -> torch.Tensor:

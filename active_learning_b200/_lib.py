@@ -16,7 +16,7 @@ ALQ_OK = 0
 ERR_NAMES = {1: "ALQ_ERR_INVALID", 2: "ALQ_ERR_CUDA", 3: "ALQ_ERR_NOMEM", 4: "ALQ_ERR_STATE",
              5: "ALQ_ERR_NUMERIC"}
 MODE_MARGIN, MODE_LEAST_CONFIDENCE, MODE_ENTROPY = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_f32p = C.c_void_p
 c_i32p = C.c_void_p
@@ -52,6 +52,7 @@ SIGNATURES = {
     "alq_destroy": (None, [C.c_void_p]),
     "alq_last_error": (C.c_char_p, [C.c_void_p]),
     "alq_launch_count": (C.c_int64, [C.c_void_p]),
+    "alq_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "alq_score_softmax": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                     c_f32p, C.c_void_p]),
     "alq_select_smallest": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, c_i32p, C.c_void_p]),

@@ -31,6 +31,8 @@ struct alq_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     int64_t launches = 0;
+    int k3_impl = 0;          // 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32
+    int greedy_variant = 0;   // 0 auto, 1 direct loads, 2 bulk-copy pipeline
     std::string err;
 };
 

@@ -4,7 +4,7 @@
 
 #include "alq_common.cuh"
 
-extern "C" int alq_version(void) { return 1; }
+extern "C" int alq_version(void) { return 2; }
 
 extern "C" int alq_create(alq_ctx** out, int device) {
     if (!out) return ALQ_ERR_INVALID;
@@ -51,6 +51,15 @@ extern "C" void alq_destroy(alq_ctx* ctx) {
 
 extern "C" const char* alq_last_error(const alq_ctx* ctx) {
     return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int alq_set_option(alq_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return ALQ_ERR_INVALID;
+    const std::string k(key);
+    if (k == "k3_impl" && value >= 0 && value <= 2) ctx->k3_impl = static_cast<int>(value);
+    else if (k == "greedy_variant" && value >= 0 && value <= 2) ctx->greedy_variant = static_cast<int>(value);
+    else ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_set_option: unknown option or value: %s=%lld", key, (long long)value);
+    return ALQ_OK;
 }
 
 extern "C" int64_t alq_launch_count(const alq_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -722,7 +722,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     const size_t smem_v1 = static_cast<size_t>(d + c) * sizeof(float);
     PipeCfg cfg{};
     size_t smem_v2 = 0;
-    int variant = D->variant;
+    int variant = D->variant ? D->variant : ctx->greedy_variant;
     {
         const size_t row_bytes = static_cast<size_t>(d + c) * 4;
         const size_t centre_bytes = static_cast<size_t>((d + c + 31) & ~31) * 4;

@@ -201,6 +201,11 @@ __global__ void __launch_bounds__(1024) argmin_kernel(const float* __restrict__ 
 
 }  // namespace
 
+int alq_min_dist_tc(alq_ctx* ctx, const float* x, int64_t ldx, const float* xn, int64_t n, const float* y,
+                    int64_t ldy, const float* yn, int64_t m, int32_t d, const float* xa, int64_t ldxa,
+                    const float* xan, const float* ya, int64_t ldya, const float* yan, int32_t c,
+                    int32_t reduce_max, int32_t accumulate, float* out, cudaStream_t st);
+
 extern "C" int alq_min_dist(alq_ctx* ctx, const float* x, int64_t ldx, const float* xn, int64_t n,
                             const float* y, int64_t ldy, const float* yn, int64_t m, int32_t d,
                             const float* xa, int64_t ldxa, const float* xan, const float* ya, int64_t ldya,
@@ -219,6 +224,19 @@ extern "C" int alq_min_dist(alq_ctx* ctx, const float* x, int64_t ldx, const flo
     if (factored && ((c % 4) || (ldxa % 4) || (ldya % 4) || !aligned16(xa) || !aligned16(ya)))
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_min_dist: c, ldxa, ldya must be multiples of 4 (pad with zeros)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // tensor-core path (tcgen05 3xTF32) for contractions big enough to amortise the operand split
+    {
+        const bool tc_shape = d >= 32 && (!factored || c >= 32) && m > 0;
+        const double flop = 2.0 * static_cast<double>(n) * static_cast<double>(m) * (d + (factored ? c : 0));
+        const bool want_tc = ctx->k3_impl == 2 || (ctx->k3_impl == 0 && flop >= 4e9);
+        if (want_tc && tc_shape) {
+            const int rc = alq_min_dist_tc(ctx, x, ldx, xn, n, y, ldy, yn, m, d, xa, ldxa, xan, ya, ldya, yan, c,
+                                           reduce_max, accumulate, out, st);
+            if (rc != ALQ_ERR_STATE) return rc;   // ALQ_ERR_STATE: not available here -> SIMT below
+        } else if (ctx->k3_impl == 2) {
+            ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_min_dist: k3_impl=2 needs d >= 32 (and c >= 32 when factored)");
+        }
+    }
     if (!accumulate) {
         fill_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(out, n, reduce_max ? -INFINITY : INFINITY);
         ALQ_LAUNCH_CHECK(ctx);

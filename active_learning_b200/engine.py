@@ -69,6 +69,10 @@ class Engine:
     def _check(self, rc, what):
         _lib.check(self.lib, self._h, rc, what)
 
+    def set_option(self, key: str, value: int):
+        """'k3_impl': 0 auto / 1 fp32 SIMT / 2 tcgen05 3xTF32;  'greedy_variant': 0 auto / 1 direct / 2 pipeline."""
+        self._check(self.lib.alq_set_option(self._h, key.encode(), int(value)), "alq_set_option")
+
     @property
     def launches(self) -> int:
         return int(self.lib.alq_launch_count(self._h))

@@ -44,6 +44,10 @@ int alq_version(void);
 int alq_create(alq_ctx** out, int device);
 void alq_destroy(alq_ctx* ctx);
 const char* alq_last_error(const alq_ctx* ctx);
+/* Implementation knobs (defaults pick the fastest valid kernel):
+ *   "k3_impl"        0 auto | 1 exact-fp32 SIMT contraction | 2 tcgen05 3xTF32 contraction
+ *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline            */
+int alq_set_option(alq_ctx* ctx, const char* key, int64_t value);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 int64_t alq_launch_count(const alq_ctx* ctx);
 

@@ -103,6 +103,49 @@ def test_min_dist_float_and_factored(eng):
     assert torch.equal(got, d2[:100, 100:].min(1).values)
 
 
+@pytest.mark.parametrize("n,m,d,c", [(300, 700, 96, 0), (1000, 1000, 2048, 0), (777, 1313, 516, 0),
+                                     (500, 600, 64, 40), (640, 900, 2048, 1000)])
+def test_min_dist_tensor_core_path(eng, n, m, d, c):
+    """tcgen05 3xTF32 contraction (k3_impl=2): bit-identical to fp32 on integer rows (lo == 0), within
+    1e-5 * (|x|^2 + |y|^2) of the fp64 truth on float rows; min and max epilogues; accumulate."""
+    rng = np.random.default_rng(n + m + d + c)
+    cu = lambda t: t.cuda()
+    try:
+        eng.set_option("k3_impl", 2)
+        for ints in (True, False):
+            if ints:
+                x = torch.from_numpy(rng.integers(-1, 2, size=(n, d)).astype(np.float32))
+                y = torch.from_numpy(rng.integers(-1, 2, size=(m, d)).astype(np.float32))
+                xa = torch.from_numpy(rng.integers(-1, 2, size=(n, max(c, 1))).astype(np.float32))
+                ya = torch.from_numpy(rng.integers(-1, 2, size=(m, max(c, 1))).astype(np.float32))
+            else:
+                x, y = torch.relu(torch.randn(n, d)), torch.relu(torch.randn(m, d))
+                xa, ya = torch.randn(n, max(c, 1)) * 0.05, torch.randn(m, max(c, 1)) * 0.05
+            dot = x.double() @ y.double().T
+            nx, ny = x.double().square().sum(1), y.double().square().sum(1)
+            args = [cu(x), eng.row_norm2(cu(x)), cu(y), eng.row_norm2(cu(y))]
+            if c:
+                dot = dot * (xa.double() @ ya.double().T)
+                nx, ny = nx * xa.double().square().sum(1), ny * ya.double().square().sum(1)
+                args += [cu(xa), eng.row_norm2(cu(xa)), cu(ya), eng.row_norm2(cu(ya))]
+            d2 = (nx[:, None] + ny[None, :]) - 2 * dot
+            tol = 0.0 if ints else 1e-5 * float(nx.max() + ny.max())
+            got = eng.min_dist(*args).cpu().double()
+            assert (got - d2.min(1).values).abs().max() <= tol
+            got = eng.min_dist(*args, reduce_max=True).cpu().double()
+            assert (got - d2.max(1).values).abs().max() <= tol
+        out = torch.full((n,), float("inf"), device="cuda")      # accumulate over column chunks
+        half = m // 2
+        for sl in (slice(0, half), slice(half, m)):
+            a2 = [args[0], args[1], args[2][sl], args[3][sl]]
+            if c:
+                a2 += [args[4], args[5], args[6][sl], args[7][sl]]
+            eng.min_dist(*a2, out=out, accumulate=True)
+        assert (out.cpu().double() - d2.min(1).values).abs().max() <= tol
+    finally:
+        eng.set_option("k3_impl", 0)
+
+
 # ------------------------------------------------------------------------------------------- K4 / K5 vs golden
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("tag", ["int", "f32"])

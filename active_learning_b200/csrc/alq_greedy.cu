@@ -58,7 +58,7 @@ __device__ __forceinline__ void finish_row(const StepArgs& A, int row, int centr
     if (row == centre) m = ALQ_NEG_INF;   // a picked row is never a candidate again
     A.mind[row] = m;
     if (SAMPLE) {
-        A.cfull[cf_off + A.vpos[row]] = fmaxf(m, 0.0f);
+        A.cfull[cf_off + A.vpos[row]] = m;          // raw running min; the sampling stage clips at 0
     } else {
         const unsigned long long k = alq_maxkey(m, static_cast<uint32_t>(row));
         best_key = k > best_key ? k : best_key;
@@ -327,6 +327,11 @@ step_pipe_kernel(StepArgs A, PipeCfg cfg) {
     }
 }
 
+__global__ void fill_f32_kernel(float* p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // t = 0 helpers
 // ------------------------------------------------------------------------------------------------
@@ -367,7 +372,7 @@ __global__ void decode_picks_kernel(const unsigned long long* best, const int* b
     if (t < budget[p]) picks[pick_off[p] + t] = static_cast<int>(alq_maxkey_row(best[i]));
 }
 
-// cfull[off[p] + vpos[i]] = clip(mind[i], 0);  posinv[...] = i
+// cfull[off[p] + vpos[i]] = mind[i] (labeled / padding slots stay -inf);  posinv[...] = i
 __global__ void __launch_bounds__(256)
 sample_setup_kernel(const float* __restrict__ mind, const int* __restrict__ vpos, const BlockSeg* segs,
                     const int* cfull_off, float* cfull, int* posinv) {
@@ -375,7 +380,7 @@ sample_setup_kernel(const float* __restrict__ mind, const int* __restrict__ vpos
     const int off = cfull_off[seg.part];
     for (int r = seg.row_lo + threadIdx.x; r < seg.row_hi; r += blockDim.x) {
         const int k = off + vpos[r];
-        cfull[k] = fmaxf(mind[r], 0.0f);
+        cfull[k] = mind[r];
         posinv[k] = r;
     }
 }
@@ -403,9 +408,6 @@ struct SampleArgs {
     const int* comb;
     float* cfull;
     const int* posinv;
-    const int* vpos;
-    const float* mind;
-    float* tmp_mind;             // [n] scratch of the NaN-retry branch
     float* leafval;              // leaf sums, same indexing as leaf_off
     double* cta_part;            // [P * kCL] per-CTA probability mass
     const double* uniforms;      // [sum budget]
@@ -436,18 +438,18 @@ __device__ __forceinline__ float leaf_sum_group(const float* a, int len, int g_l
     if (len < 8) {
         res = 0.f;
         if (g_lane == 0)
-            for (int i = 0; i < len; ++i) res += a[i];
+            for (int i = 0; i < len; ++i) res += fmaxf(a[i], 0.f);
         return res;
     }
     const int stop = len - (len & 7);
-    float r = a[g_lane];
-    for (int i = 8; i < stop; i += 8) r += a[i + g_lane];
+    float r = fmaxf(a[g_lane], 0.f);                 // prob = clip(min_dist, 0) (coreset_sampler.py:84)
+    for (int i = 8; i < stop; i += 8) r += fmaxf(a[i + g_lane], 0.f);
     r = r + __shfl_down_sync(gmask, r, 1, 8);   // lanes 0,2,4,6: r0+r1, r2+r3, ...
     r = r + __shfl_down_sync(gmask, r, 2, 8);   // lanes 0,4
     r = r + __shfl_down_sync(gmask, r, 4, 8);   // lane 0
     res = r;
     if (g_lane == 0)
-        for (int i = stop; i < len; ++i) res += a[i];
+        for (int i = stop; i < len; ++i) res += fmaxf(a[i], 0.f);
     return res;
 }
 
@@ -515,13 +517,12 @@ sample_cluster_kernel(SampleArgs A) {
             return;                                              // same decision in every CTA
         }
         // ---- sum == 0 -> prob is NaN -> `min_dist_labeled += 0.00001` and retry (:87-90) --------
-        const int rows = S.row_hi - S.row_lo, per_rows = (rows + kCL - 1) / kCL;
-        const int r_lo = S.row_lo + rank * per_rows, r_hi = min(S.row_hi, r_lo + per_rows);
-        for (int r = r_lo + threadIdx.x; r < r_hi; r += kSampThreads) {
-            const float m = (attempt == 0 ? A.mind[r] : A.tmp_mind[r]) + 0.00001f;
-            A.tmp_mind[r] = m;
-            cf[A.vpos[r]] = fmaxf(m, 0.0f);
-        }
+        // In place: labeled / picked slots hold -inf and stay there; candidate slots are rewritten from
+        // `mind` by the next step kernel, so the bump never outlives this draw (like the reference's
+        // per-step temporary).
+        const int npad_r = (n + 3) & ~3, per_r = (npad_r + kCL - 1) / kCL;
+        for (int k = rank * per_r + threadIdx.x; k < min(npad_r, (rank + 1) * per_r); k += kSampThreads)
+            cf[k] = cf[k] + 0.00001f;
         cluster_sync_all();
     }
 
@@ -536,10 +537,10 @@ sample_cluster_kernel(SampleArgs A) {
         const int base = my_lo + j;
         if (base < npad) {
             const float4 c4 = *reinterpret_cast<const float4*>(cf + base);   // zero padded to x4
-            loc += static_cast<double>(c4.x / total32);
-            loc += static_cast<double>(c4.y / total32);
-            loc += static_cast<double>(c4.z / total32);
-            loc += static_cast<double>(c4.w / total32);
+            loc += static_cast<double>(fmaxf(c4.x, 0.f) / total32);
+            loc += static_cast<double>(fmaxf(c4.y, 0.f) / total32);
+            loc += static_cast<double>(fmaxf(c4.z, 0.f) / total32);
+            loc += static_cast<double>(fmaxf(c4.w, 0.f) / total32);
         }
     }
     double inc = loc;                                               // inclusive scan inside the warp
@@ -579,7 +580,7 @@ sample_cluster_kernel(SampleArgs A) {
         for (int j = 0; j < E && hit < 0; ++j) {
             const int k = my_lo + j;
             if (k >= n) break;
-            const float c = cf[k];
+            const float c = fmaxf(cf[k], 0.f);
             if (c > 0.f) last_nz = k;
             run += static_cast<double>(c / total32);
             if ((run / total) > u) hit = k;
@@ -807,7 +808,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
                                       sched.size() * sizeof(PartSched), leaf_off_all.size() * 4 + 4,
                                       level_off_all.size() * 4 + 4, comb_all.size() * 4 + 4,
                                       static_cast<size_t>(cfull_total) * 4 + 16, static_cast<size_t>(cfull_total) * 4 + 16,
-                                      sample ? static_cast<size_t>(n) * 4 : 0, leaf_off_all.size() * 4 + 4,
+                                      leaf_off_all.size() * 4 + 4,
                                       static_cast<size_t>(P) * kCL * 8, 64});
     int rc = alq_scratch_reserve(ctx, need);
     if (rc) return rc;
@@ -826,7 +827,6 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     int* d_comb = cur.take<int>(comb_all.size() + 1);
     float* d_cfull = cur.take<float>(cfull_total + 4);
     int* d_posinv = cur.take<int>(cfull_total + 4);
-    float* d_tmp_mind = cur.take<float>(sample ? n : 0);
     float* d_leafval = cur.take<float>(leaf_off_all.size() + 1);
     double* d_cta_part = cur.take<double>(static_cast<size_t>(P) * kCL);
     int* d_status = cur.take<int>(1);
@@ -846,7 +846,8 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         ALQ_CUDA(ctx, cudaMemcpyAsync(d_level_off, level_off_all.data(), level_off_all.size() * 4, cudaMemcpyHostToDevice, st));
         if (!comb_all.empty())
             ALQ_CUDA(ctx, cudaMemcpyAsync(d_comb, comb_all.data(), comb_all.size() * 4, cudaMemcpyHostToDevice, st));
-        ALQ_CUDA(ctx, cudaMemsetAsync(d_cfull, 0, static_cast<size_t>(cfull_total + 4) * 4, st));
+        fill_f32_kernel<<<(cfull_total + 4 + 255) / 256, 256, 0, st>>>(d_cfull, cfull_total + 4, -INFINITY);
+        ALQ_LAUNCH_CHECK(ctx);
         ALQ_CUDA(ctx, cudaMemsetAsync(d_posinv, 0xff, static_cast<size_t>(cfull_total + 4) * 4, st));
     } else {
         ALQ_CUDA(ctx, cudaMemsetAsync(d_best, 0, n_best * 8, st));
@@ -872,8 +873,8 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     size_t samp_smem = 0;
     if (sample) {
         SA.sched = d_sched; SA.leaf_off = d_leaf_off; SA.level_off = d_level_off; SA.comb = d_comb;
-        SA.cfull = d_cfull; SA.posinv = d_posinv; SA.vpos = D->vpos; SA.mind = D->mind;
-        SA.tmp_mind = d_tmp_mind; SA.leafval = d_leafval; SA.cta_part = d_cta_part; SA.uniforms = d_unif; SA.first_pick = d_first; SA.cur = d_cur;
+        SA.cfull = d_cfull; SA.posinv = d_posinv;
+        SA.leafval = d_leafval; SA.cta_part = d_cta_part; SA.uniforms = d_unif; SA.first_pick = d_first; SA.cur = d_cur;
         SA.picks = D->picks; SA.status = d_status;
         samp_smem = static_cast<size_t>(max_nodes) * sizeof(float);
         if (samp_smem > 32 * 1024)

@@ -183,27 +183,7 @@ __device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long lon
     if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
 }
 
-// Whole array (npad = power of two <= 16384) inside one CTA's shared memory.
-__global__ void __launch_bounds__(1024)
-sort_single_cta_kernel(const unsigned long long* __restrict__ keys, int64_t b, int npad,
-                       int32_t* __restrict__ out_pos) {
-    extern __shared__ unsigned long long sk[];
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) sk[i] = i < b ? keys[i] : ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const bool up = (lo & k) == 0;
-                cmpxchg(sk[lo], sk[lo | j], up);
-            }
-            __syncthreads();
-        }
-    }
-    for (int i = threadIdx.x; i < b; i += blockDim.x) out_pos[i] = static_cast<int32_t>(sk[i] & 0xffffffffu);
-}
-
-// General path for B > 16384: tiles of 4096 keys in shared memory + global exchange steps.
+// General path for B > 65536: tiles of 4096 keys in shared memory + global exchange steps.
 constexpr int kTile = 4096;
 
 __global__ void __launch_bounds__(1024)
@@ -275,7 +255,7 @@ sort_runs_kernel(unsigned long long* __restrict__ keys, int64_t b) {
 
 __global__ void __launch_bounds__(256)
 merge_rank_kernel(const unsigned long long* __restrict__ keys, int64_t b, int runs,
-                  int32_t* __restrict__ out_pos) {
+                  int32_t* __restrict__ out_pos, int64_t keep) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= b) return;
     const unsigned long long key = keys[i];
@@ -292,7 +272,21 @@ merge_rank_kernel(const unsigned long long* __restrict__ keys, int64_t b, int ru
         }
         rank += lo;
     }
-    out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
+    if (rank < keep) out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
+}
+
+// multi-GPU merge helpers -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+topb_pack_kernel(const float* __restrict__ scores, const int32_t* __restrict__ pos, int64_t k, int64_t row_lo,
+                 int64_t b_pad, unsigned long long* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= b_pad) return;
+    unsigned long long v = ~0ull;
+    if (i < k) {
+        const int32_t p = pos[i];
+        v = (static_cast<unsigned long long>(score_key(scores[p])) << 32) | static_cast<uint32_t>(row_lo + p);
+    }
+    out[i] = v;
 }
 
 int64_t next_pow2(int64_t v) {
@@ -349,7 +343,7 @@ extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n,
         const int runs = static_cast<int>((b + kRun - 1) / kRun);
         sort_runs_kernel<<<runs, 1024, 0, st>>>(keys, b);
         ALQ_LAUNCH_CHECK(ctx);
-        merge_rank_kernel<<<static_cast<int>((b + 255) / 256), 256, 0, st>>>(keys, b, runs, out_pos);
+        merge_rank_kernel<<<static_cast<int>((b + 255) / 256), 256, 0, st>>>(keys, b, runs, out_pos, b);
         ALQ_LAUNCH_CHECK(ctx);
     } else {
         sort_pad_kernel<<<static_cast<int>((npad + 1023) / 1024), 1024, 0, st>>>(keys, b, npad);
@@ -369,6 +363,39 @@ extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n,
         sort_emit_kernel<<<static_cast<int>((b + 255) / 256), 256, 0, st>>>(keys, b, out_pos);
         ALQ_LAUNCH_CHECK(ctx);
     }
+    return ALQ_OK;
+}
+
+// ---- multi-GPU: every rank contributes its local top-B as packed (score key, global position) words;
+//      after one all-gather each rank merges the G*B words with the same run-sort + rank-merge.
+extern "C" int alq_topb_pack(alq_ctx* ctx, const float* scores, const int32_t* pos, int64_t k, int64_t row_lo,
+                             int64_t b_pad, uint64_t* out, void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (k < 0 || b_pad < k || row_lo < 0 || row_lo + (1LL << 31) > (1LL << 32) || !out || (k > 0 && (!scores || !pos)))
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_topb_pack: bad arguments");
+    if (b_pad == 0) return ALQ_OK;
+    topb_pack_kernel<<<static_cast<int>((b_pad + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        scores, pos, k, row_lo, b_pad, reinterpret_cast<unsigned long long*>(out));
+    ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}
+
+extern "C" int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int64_t b, int32_t* out_gpos,
+                              void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (n < 0 || b < 0 || b > n || n > (1 << 24) || !keys || !out_gpos)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_topb_merge: bad arguments (n=%lld b=%lld)", (long long)n, (long long)b);
+    if (b == 0) return ALQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = alq_scratch_reserve(ctx, scratch_need({static_cast<size_t>(n) * 8}));
+    if (rc) return rc;
+    unsigned long long* work = ScratchCursor(ctx->scratch).take<unsigned long long>(n);
+    ALQ_CUDA(ctx, cudaMemcpyAsync(work, keys, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToDevice, st));
+    const int runs = static_cast<int>((n + kRun - 1) / kRun);
+    sort_runs_kernel<<<runs, 1024, 0, st>>>(work, n);
+    ALQ_LAUNCH_CHECK(ctx);
+    merge_rank_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(work, n, runs, out_gpos, b);
+    ALQ_LAUNCH_CHECK(ctx);
     return ALQ_OK;
 }
 

@@ -95,6 +95,22 @@ class Engine:
                                                  self._stream()), "alq_select_smallest")
         return out
 
+    def topb_pack(self, scores: torch.Tensor, pos: torch.Tensor, row_lo: int, b_pad: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Local winners as packed (score key << 32 | global position) int64 words, ~0-padded to b_pad."""
+        if out is None:
+            out = torch.empty(int(b_pad), dtype=torch.int64, device=scores.device)
+        self._check(self.lib.alq_topb_pack(self._h, _ptr(scores), _ptr(pos), pos.numel(), int(row_lo), int(b_pad),
+                                           _ptr(out), self._stream()), "alq_topb_pack")
+        return out
+
+    def topb_merge(self, keys: torch.Tensor, b: int) -> torch.Tensor:
+        """Global positions (int32) of the b smallest packed words, ascending."""
+        out = torch.empty(int(b), dtype=torch.int32, device=keys.device)
+        self._check(self.lib.alq_topb_merge(self._h, _ptr(keys), keys.numel(), int(b), _ptr(out), self._stream()),
+                    "alq_topb_merge")
+        return out
+
     def uncertainty_query_host(self, logits_host: torch.Tensor, mode: int, b: int) -> np.ndarray:
         """Host-buffer entry point (H2D + K1 + K1b + D2H inside the library)."""
         if logits_host.is_cuda or logits_host.dtype != torch.float32 or not logits_host.is_contiguous():

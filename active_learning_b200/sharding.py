@@ -22,6 +22,7 @@ class ShardGroup:
         self.pg = process_group
         self.rank = dist.get_rank(process_group)
         self.world_size = dist.get_world_size(process_group)
+        self._buf = {}
 
     # ---- row sharding (K1 / K2) -----------------------------------------------------------------
     def row_range(self, n, rank=None):
@@ -34,30 +35,21 @@ class ShardGroup:
     def merge_smallest(self, scores_local, pos_local, row_lo, budget, engine):
         """Global `budget` smallest (score, global position) pairs from every rank's local winners.
 
-        scores_local: this rank's score vector; pos_local: its local top-B positions in ascending
-        (score, position) order (K1b output); row_lo: global position of local row 0.
-        The gathered array is ordered by rank and, inside a rank, by (score, position); ranks own
-        ascending position ranges, so among equal scores array order == global-position order and
-        K1b's "lowest array position first" tie-break IS the global tie-break.  The merge is one
-        more K1b launch over G*B candidates; only the B winners go to the host."""
-        dev = scores_local.device
+        scores_local: this rank's score vector; pos_local: its local top-B positions (K1b output);
+        row_lo: global position of local row 0.  Each rank packs its winners into 64-bit words
+        (order-preserving score key << 32 | global position), ONE all-gather moves G*B words, and
+        every rank runs the same device merge: ascending words == ascending (score, position), i.e.
+        exactly the single-GPU K1b order.  Only the B winning positions go to the host."""
         b = int(budget)
-        k = int(pos_local.numel())
-        s = torch.full((b,), float("inf"), dtype=torch.float32, device=dev)
-        g = torch.full((b,), -1, dtype=torch.int64, device=dev)
-        if k:
-            idx = pos_local.long()
-            s[:k] = scores_local[idx]
-            g[:k] = idx + int(row_lo)
-        s_all = [torch.empty_like(s) for _ in range(self.world_size)]
-        g_all = [torch.empty_like(g) for _ in range(self.world_size)]
-        dist.all_gather(s_all, s, group=self.pg)
-        dist.all_gather(g_all, g, group=self.pg)
-        s_cat, g_cat = torch.cat(s_all), torch.cat(g_all)
-        sel = engine.select_smallest(s_cat, b)
-        out = g_cat[sel.long()].cpu().numpy()
-        assert (out >= 0).all()
-        return out
+        key = (b, scores_local.device)
+        if self._buf.get("key") != key:
+            self._buf = {"key": key,
+                         "mine": torch.empty(b, dtype=torch.int64, device=scores_local.device),
+                         "all": torch.empty(b * self.world_size, dtype=torch.int64, device=scores_local.device)}
+        mine, allk = self._buf["mine"], self._buf["all"]
+        engine.topb_pack(scores_local, pos_local, row_lo, b, out=mine)
+        dist.all_gather_into_tensor(allk, mine, group=self.pg)
+        return engine.topb_merge(allk, b).cpu().numpy().astype(np.int64) & 0xFFFFFFFF
 
     # ---- partition dealing ------------------------------------------------------------------------
     def my_partitions(self, n_parts, rank=None):

@@ -81,6 +81,23 @@ class OracleEngine:
     def select_smallest(self, scores, b):
         return torch.from_numpy(O.select_smallest(scores, int(b)).astype(np.int32))
 
+    def topb_pack(self, scores, pos, row_lo, b_pad, out=None):
+        s = (scores.numpy().astype(np.float32) + np.float32(0.0)).view(np.uint32).astype(np.uint64)
+        neg = (s >> np.uint64(31)).astype(bool)
+        s = np.where(neg, ~s & np.uint64(0xFFFFFFFF), s | np.uint64(0x80000000))
+        p = pos.numpy().astype(np.int64)
+        words = np.full(int(b_pad), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+        words[:len(p)] = (s[p] << np.uint64(32)) | (p + int(row_lo)).astype(np.uint64)
+        t = torch.from_numpy(words.view(np.int64).copy())
+        if out is not None:
+            out.copy_(t)
+            return out
+        return t
+
+    def topb_merge(self, keys, b):
+        w = np.sort(keys.numpy().view(np.uint64))[:int(b)]
+        return torch.from_numpy((w & np.uint64(0xFFFFFFFF)).astype(np.int64).astype(np.int32))
+
     def badge_factors(self, logits, batch_size):
         a = O.badge_factors(logits, int(batch_size))
         cpad = (a.shape[1] + 3) & ~3

@@ -154,3 +154,19 @@ def test_full_size_margin_properties(eng):
     sub = np.random.default_rng(0).choice(80000, 2000, replace=False)
     ref = O.softmax_scores(logits[torch.from_numpy(sub).cuda()].cpu(), O.MODE_MARGIN).numpy()
     np.testing.assert_allclose(s[sub], ref, rtol=0, atol=TOL_PROB)
+
+
+def test_topb_pack_merge_equals_global_select(eng):
+    """The multi-GPU merge primitive without the all-gather: shard a score vector in 3, pack each
+    shard's local top-B, merge the packed words -> the single-GPU K1b result (ties included)."""
+    rng = np.random.default_rng(11)
+    n, b = 90000, 7000
+    scores = torch.from_numpy((rng.integers(0, 400, size=n) / 128.0).astype(np.float32)).cuda()
+    bounds = [0, 30000, 61000, n]
+    words = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        loc = scores[lo:hi].contiguous()
+        pos = eng.select_smallest(loc, min(b, hi - lo))
+        words.append(eng.topb_pack(loc, pos, lo, b))
+    got = eng.topb_merge(torch.cat(words), b).cpu().numpy()
+    assert np.array_equal(got, eng.select_smallest(scores, b).cpu().numpy())

@@ -116,6 +116,113 @@ score_rows_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_
     }
 }
 
+__device__ __forceinline__ float batch_scale(int64_t row, int64_t n, int bs) {
+    const int64_t tail = n % bs;
+    const int64_t cut = n - tail;
+    return 1.0f / static_cast<float>(row < cut ? bs : static_cast<int>(tail));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 / K2, pipelined: one CTA per SM, a producer lane streams tiles of contiguous rows into a ring of
+// shared-memory stages with cp.async.bulk (TMA bulk copy, mbarrier complete_tx); every consumer warp
+// owns whole tiles, pulls each row smem -> registers and runs the same row code as the direct kernel.
+// ~200 KB of loads in flight per SM independent of register pressure: this is what took the step
+// kernel of alq_greedy.cu to 0.93-0.97 of the HBM peak.
+// ---------------------------------------------------------------------------------------------
+struct RowPipeCfg {
+    int rows_per_tile, stages, consumers, tile_floats;
+};
+
+template <int NV>
+__device__ __forceinline__ void load_row_smem(const float4* p, int lane, int nvec, float4 (&v)[NV]) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int idx = lane + 32 * k;
+        v[k] = idx < nvec ? p[idx] : make_float4(ALQ_NEG_INF, ALQ_NEG_INF, ALQ_NEG_INF, ALQ_NEG_INF);
+    }
+}
+
+// MODE 0..2: scores; MODE 3: BADGE factors (writes a[row, :] and a_norm2[row])
+template <int NV, int MODE>
+__global__ void __launch_bounds__(32 * 17, 1)
+rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg cfg, float* __restrict__ scores,
+                 int bs, float* __restrict__ a, int64_t lda) {
+    extern __shared__ __align__(128) unsigned char smem_rows[];
+    float* tiles = reinterpret_cast<float*>(smem_rows);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(cfg.stages) * cfg.tile_floats);
+    uint64_t* empty = full + cfg.stages;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int R = cfg.rows_per_tile;
+    // contiguous share of the rows for this CTA, in whole tiles
+    const int64_t tiles_total = (n + R - 1) / R;
+    const int64_t t_lo = tiles_total * blockIdx.x / gridDim.x, t_hi = tiles_total * (blockIdx.x + 1) / gridDim.x;
+    const int ntiles = static_cast<int>(t_hi - t_lo);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nvec = c >> 2;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % cfg.stages;
+                const uint32_t round = static_cast<uint32_t>(i / cfg.stages);
+                if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);
+                const int64_t row0 = (t_lo + i) * R;
+                const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
+                const uint32_t bytes = static_cast<uint32_t>(rr) * static_cast<uint32_t>(c) * 4u;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(tiles + static_cast<size_t>(s) * cfg.tile_floats, logits + row0 * c, bytes, &full[s]);
+            }
+        }
+    } else {
+        const int cw = warp - 1;
+        for (int i = cw; i < ntiles; i += cfg.consumers) {
+            const int s = i % cfg.stages;
+            const int64_t row0 = (t_lo + i) * R;
+            const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
+            mbar_wait(&full[s], static_cast<uint32_t>(i / cfg.stages) & 1u);
+            const float* tile = tiles + static_cast<size_t>(s) * cfg.tile_floats;
+            float my_score = 0.f;
+            for (int r = 0; r < rr; ++r) {
+                float4 v[NV];
+                load_row_smem<NV>(reinterpret_cast<const float4*>(tile + static_cast<size_t>(r) * c), lane, nvec, v);
+                if (MODE < 3) {
+                    const RowStats st = row_stats_vec<NV, MODE == ALQ_MODE_MARGIN, false, MODE == ALQ_MODE_ENTROPY>(v, lane, nvec);
+                    if (lane == r) my_score = score_from_stats(st, MODE);
+                } else {
+                    const RowStats st = row_stats_vec<NV, false, true, false>(v, lane, nvec);
+                    const int64_t row = row0 + r;
+                    const float inv_bs = batch_scale(row, n, bs);
+                    float4* q = reinterpret_cast<float4*>(a + row * lda);
+                    float nn = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        const int idx = lane + 32 * k;
+                        if (idx < nvec) {
+                            float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float pj = exp_neg(e[j] - st.m) / st.s;
+                                const float g = (pj - ((idx * 4 + j) == st.arg ? 1.0f : 0.0f)) * inv_bs;
+                                e[j] = g;
+                                nn += g * g;
+                            }
+                            q[idx] = make_float4(e[0], e[1], e[2], e[3]);
+                        }
+                    }
+                    nn = warp_sum(nn);
+                    if (lane == r) my_score = nn;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);       // all smem reads of this stage are done
+            if (lane < rr) scores[row0 + lane] = my_score;
+        }
+    }
+}
+
 // Any c / alignment: two passes over the row, the second one hits L1/L2.
 __global__ void __launch_bounds__(kScoreThreads)
 score_rows_generic_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int mode,
@@ -151,12 +258,6 @@ score_rows_generic_kernel(const float* __restrict__ logits, int64_t n, int c, in
 // ---------------------------------------------------------------------------------------------
 // K2: a = (softmax - onehot(argmax)) * (1 / bs_i)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float batch_scale(int64_t row, int64_t n, int bs) {
-    const int64_t tail = n % bs;
-    const int64_t cut = n - tail;
-    return 1.0f / static_cast<float>(row < cut ? bs : static_cast<int>(tail));
-}
-
 template <int NV>
 __global__ void __launch_bounds__(kScoreThreads)
 badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs,
@@ -327,6 +428,44 @@ int rows_grid(const alq_ctx* ctx, int64_t n, int warps_per_block) {
     return static_cast<int>(need < cap ? need : cap);
 }
 
+// shared-memory plan of the pipelined kernels; false if the row does not fit
+bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem) {
+    const size_t row_bytes = static_cast<size_t>(c) * 4;
+    if (row_bytes % 16 || row_bytes > 16384 || ctx->smem_optin < 64 * 1024) return false;
+    int R = static_cast<int>(std::max<size_t>(1, 16384 / row_bytes));
+    R = std::min(R, 32);
+    const size_t tile = R * row_bytes;
+    int stages = static_cast<int>((ctx->smem_optin - 4096) / tile);
+    stages = std::min(stages, 16);
+    if (stages < 3) return false;
+    cfg.rows_per_tile = R; cfg.stages = stages; cfg.consumers = stages; cfg.tile_floats = static_cast<int>(tile / 4);
+    smem = stages * tile + 2 * stages * sizeof(uint64_t) + 128;
+    return true;
+}
+
+template <int NV, int MODE>
+cudaError_t launch_rows_pipe(const alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
+                             int64_t n, int c, float* scores, int bs, float* a, int64_t lda) {
+    cudaError_t e = cudaFuncSetAttribute(rows_pipe_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const int64_t tiles_total = (n + cfg.rows_per_tile - 1) / cfg.rows_per_tile;
+    const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles_total));
+    rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, a, lda);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_rows_pipe_nv(const alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
+                                int64_t n, int c, float* scores, int bs, float* a, int64_t lda) {
+    const int nv = (c / 4 + 31) / 32;
+    if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
+    if (nv <= 2) return launch_rows_pipe<2, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
+    if (nv <= 4) return launch_rows_pipe<4, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
+    if (nv <= 8) return launch_rows_pipe<8, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
+    return launch_rows_pipe<16, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
+}
+
 template <int NV>
 void launch_score_vec(int mode, int grid, cudaStream_t st, const float* logits, int64_t n, int c,
                       int64_t ld, float* scores) {
@@ -352,6 +491,17 @@ extern "C" int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = rows_grid(ctx, n, kScoreThreads / 32);
     const bool vec = (c % 4 == 0) && (ld % 4 == 0) && aligned16(logits) && c <= 2048;
+    RowPipeCfg cfg{};
+    size_t smem = 0;
+    if (vec && ld == c && n >= 4096 && ctx->greedy_variant != 1 && plan_row_pipe(ctx, c, cfg, smem)) {
+        cudaError_t e;
+        if (mode == ALQ_MODE_MARGIN) e = launch_rows_pipe_nv<ALQ_MODE_MARGIN>(ctx, st, cfg, smem, logits, n, c, scores, 1, nullptr, 0);
+        else if (mode == ALQ_MODE_LEAST_CONFIDENCE) e = launch_rows_pipe_nv<ALQ_MODE_LEAST_CONFIDENCE>(ctx, st, cfg, smem, logits, n, c, scores, 1, nullptr, 0);
+        else e = launch_rows_pipe_nv<ALQ_MODE_ENTROPY>(ctx, st, cfg, smem, logits, n, c, scores, 1, nullptr, 0);
+        ctx->launches++;
+        if (e != cudaSuccess) ALQ_FAIL(ctx, ALQ_ERR_CUDA, "rows_pipe_kernel launch failed: %s", cudaGetErrorString(e));
+        return ALQ_OK;
+    }
     if (vec) {
         const int nv = (c / 4 + 31) / 32;
         if (nv <= 1) launch_score_vec<1>(mode, grid, st, logits, n, c, ld, scores);
@@ -380,6 +530,14 @@ extern "C" int alq_badge_factors(alq_ctx* ctx, const float* logits, int64_t n, i
     const int grid = rows_grid(ctx, n, kScoreThreads / 32);
     const bool vec = (c % 4 == 0) && (ld % 4 == 0) && (lda % 4 == 0) && aligned16(logits) &&
                      aligned16(a) && c <= 2048;
+    RowPipeCfg cfg{};
+    size_t smem = 0;
+    if (vec && ld == c && n >= 4096 && ctx->greedy_variant != 1 && plan_row_pipe(ctx, c, cfg, smem)) {
+        cudaError_t e = launch_rows_pipe_nv<3>(ctx, st, cfg, smem, logits, n, c, a_norm2, batch_size, a, lda);
+        ctx->launches++;
+        if (e != cudaSuccess) ALQ_FAIL(ctx, ALQ_ERR_CUDA, "rows_pipe_kernel launch failed: %s", cudaGetErrorString(e));
+        return ALQ_OK;
+    }
     if (vec) {
         const int nv = (c / 4 + 31) / 32;
         if (nv <= 1) badge_factors_vec_kernel<1><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);

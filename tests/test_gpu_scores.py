@@ -170,3 +170,24 @@ def test_topb_pack_merge_equals_global_select(eng):
         words.append(eng.topb_pack(loc, pos, lo, b))
     got = eng.topb_merge(torch.cat(words), b).cpu().numpy()
     assert np.array_equal(got, eng.select_smallest(scores, b).cpu().numpy())
+
+
+@pytest.mark.parametrize("n,c", [(5003, 1000), (4097, 2048), (9000, 64), (70001, 4), (6000, 1024)])
+def test_pipelined_rows_kernels_equal_direct_kernels(eng, n, c):
+    """K1/K2 TMA bulk-copy pipeline (n >= 4096, contiguous rows) vs the direct-load kernels: same row
+    code, so scores and BADGE factors must be bit-identical; and both match the oracle."""
+    torch.manual_seed(n + c)
+    logits = torch.randn(n, c) * 3
+    dev = logits.cuda()
+    try:
+        res = {}
+        for variant in (1, 0):
+            eng.set_option("greedy_variant", variant)
+            res[variant] = [eng.score_softmax(dev, m).cpu() for m in (0, 1, 2)] + \
+                [t.cpu() for t in eng.badge_factors(dev, 128)]
+    finally:
+        eng.set_option("greedy_variant", 0)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
+    assert torch.allclose(res[0][0], O.softmax_scores(logits, O.MODE_MARGIN), rtol=0, atol=TOL_PROB)
+    assert torch.allclose(res[0][3][:, :c], O.badge_factors(logits, 128), rtol=0, atol=1e-7)

@@ -32,7 +32,7 @@ class ShardGroup:
         lo = r * base + min(r, rem)
         return lo, lo + base + (1 if r < rem else 0)
 
-    def merge_smallest(self, scores_local, pos_local, row_lo, budget, engine):
+    def merge_smallest(self, scores_local, pos_local, row_lo, budget, engine, to_host=True):
         """Global `budget` smallest (score, global position) pairs from every rank's local winners.
 
         scores_local: this rank's score vector; pos_local: its local top-B positions (K1b output);
@@ -49,7 +49,10 @@ class ShardGroup:
         mine, allk = self._buf["mine"], self._buf["all"]
         engine.topb_pack(scores_local, pos_local, row_lo, b, out=mine)
         dist.all_gather_into_tensor(allk, mine, group=self.pg)
-        return engine.topb_merge(allk, b).cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        out = engine.topb_merge(allk, b)          # int32 device tensor of global positions
+        if not to_host:
+            return out
+        return out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
 
     # ---- partition dealing ------------------------------------------------------------------------
     def my_partitions(self, n_parts, rank=None):

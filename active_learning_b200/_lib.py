@@ -16,7 +16,7 @@ ALQ_OK = 0
 ERR_NAMES = {1: "ALQ_ERR_INVALID", 2: "ALQ_ERR_CUDA", 3: "ALQ_ERR_NOMEM", 4: "ALQ_ERR_STATE",
              5: "ALQ_ERR_NUMERIC"}
 MODE_MARGIN, MODE_LEAST_CONFIDENCE, MODE_ENTROPY = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_f32p = C.c_void_p
 c_i32p = C.c_void_p
@@ -41,6 +41,8 @@ class GreedyDesc(C.Structure):
         ("first_pick_host", C.c_void_p),
         ("picks", C.c_void_p),
         ("variant", C.c_int32),
+        ("shard_off_host", C.c_void_p),
+        ("vpos_all", C.c_void_p),
         ("step_kernel_ms_host", C.c_void_p),
     ]
 
@@ -53,6 +55,9 @@ SIGNATURES = {
     "alq_last_error": (C.c_char_p, [C.c_void_p]),
     "alq_launch_count": (C.c_int64, [C.c_void_p]),
     "alq_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "alq_comm_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_size_t, C.c_void_p]),
+    "alq_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "alq_comm_destroy": (C.c_int, [C.c_void_p]),
     "alq_score_softmax": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                     c_f32p, C.c_void_p]),
     "alq_select_smallest": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, c_i32p, C.c_void_p]),
@@ -61,7 +66,7 @@ SIGNATURES = {
     "alq_uncertainty_query_host": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int32,
                                              C.c_int64, c_i32p]),
     "alq_badge_factors": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
-                                    c_f32p, C.c_int64, c_f32p, C.c_void_p]),
+                                    C.c_int64, C.c_int64, c_f32p, C.c_int64, c_f32p, C.c_void_p]),
     "alq_badge_pooled_embedding": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64,
                                              C.c_int32, c_f32p, C.c_int32, C.c_int64, c_f32p,
                                              C.c_int64, C.c_void_p]),

@@ -16,6 +16,17 @@
 #error "libalq is written for sm_100a (B200) only"
 #endif
 
+constexpr int ALQ_MAX_WORLD = 8;
+
+struct AlqComm {            // peer-memory group (alq_comm.cu)
+    int world = 1, rank = 0;
+    char* window = nullptr;           // this rank's window (peers write into it)
+    char* peer[ALQ_MAX_WORLD] = {};   // mapped windows, peer[rank] == window
+    size_t bytes = 0;
+    unsigned long long epoch = 0;     // bumped per collective call: flags are epoch-tagged, never reset
+    bool connected = false;
+};
+
 struct alq_ctx {
     int device = 0;
     int sm_count = 148;
@@ -31,6 +42,7 @@ struct alq_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     int64_t launches = 0;
+    AlqComm comm;
     int k3_impl = 0;          // 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32
     int greedy_variant = 0;   // 0 auto, 1 direct loads, 2 bulk-copy pipeline
     std::string err;

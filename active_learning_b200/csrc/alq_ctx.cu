@@ -4,7 +4,7 @@
 
 #include "alq_common.cuh"
 
-extern "C" int alq_version(void) { return 2; }
+extern "C" int alq_version(void) { return 3; }
 
 extern "C" int alq_create(alq_ctx** out, int device) {
     if (!out) return ALQ_ERR_INVALID;
@@ -39,6 +39,7 @@ extern "C" int alq_create(alq_ctx** out, int device) {
 extern "C" void alq_destroy(alq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    alq_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->arena2) cudaFree(ctx->arena2);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -116,6 +116,7 @@ score_rows_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_
     }
 }
 
+// `row` and `n` are positions in the loader order of the WHOLE pool (a shard passes its row offset)
 __device__ __forceinline__ float batch_scale(int64_t row, int64_t n, int bs) {
     const int64_t tail = n % bs;
     const int64_t cut = n - tail;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void load_row_smem(const float4* p, int lane, int nve
 template <int NV, int MODE>
 __global__ void __launch_bounds__(32 * 17, 1)
 rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg cfg, float* __restrict__ scores,
-                 int bs, float* __restrict__ a, int64_t lda) {
+                 int bs, int64_t grow0, int64_t n_total, float* __restrict__ a, int64_t lda) {
     extern __shared__ __align__(128) unsigned char smem_rows[];
     float* tiles = reinterpret_cast<float*>(smem_rows);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(cfg.stages) * cfg.tile_floats);
@@ -194,7 +195,7 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
                 } else {
                     const RowStats st = row_stats_vec<NV, false, true, false>(v, lane, nvec);
                     const int64_t row = row0 + r;
-                    const float inv_bs = batch_scale(row, n, bs);
+                    const float inv_bs = batch_scale(grow0 + row, n_total, bs);
                     float4* q = reinterpret_cast<float4*>(a + row * lda);
                     float nn = 0.f;
 #pragma unroll
@@ -260,8 +261,8 @@ score_rows_generic_kernel(const float* __restrict__ logits, int64_t n, int c, in
 // ---------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(kScoreThreads)
-badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs,
-                         float* __restrict__ a, int64_t lda, float* __restrict__ a_norm2) {
+badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs, int64_t row0,
+                         int64_t n_total, float* __restrict__ a, int64_t lda, float* __restrict__ a_norm2) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -271,7 +272,7 @@ badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int
         float4 v[NV];
         load_row_vec<NV>(p, lane, nvec, v);
         const RowStats r = row_stats_vec<NV, false, true, false>(v, lane, nvec);
-        const float inv_bs = batch_scale(row, n, bs);
+        const float inv_bs = batch_scale(row0 + row, n_total, bs);
         float4* q = reinterpret_cast<float4*>(a + row * lda);
         float nn = 0.f;
 #pragma unroll
@@ -295,8 +296,8 @@ badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int
 }
 
 __global__ void __launch_bounds__(kScoreThreads)
-badge_factors_generic_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs,
-                             float* __restrict__ a, int64_t lda, int cpad,
+badge_factors_generic_kernel(const float* __restrict__ logits, int64_t n, int c, int64_t ld, int bs, int64_t row0,
+                             int64_t n_total, float* __restrict__ a, int64_t lda, int cpad,
                              float* __restrict__ a_norm2) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -318,7 +319,7 @@ badge_factors_generic_kernel(const float* __restrict__ logits, int64_t n, int c,
         float s = 0.f;
         for (int j = lane; j < c; j += 32) s += exp_neg(p[j] - m);
         s = warp_sum(s);
-        const float inv_bs = batch_scale(row, n, bs);
+        const float inv_bs = batch_scale(row0 + row, n_total, bs);
         float nn = 0.f;
         for (int j = lane; j < cpad; j += 32) {
             float g = 0.f;
@@ -445,25 +446,25 @@ bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem) {
 
 template <int NV, int MODE>
 cudaError_t launch_rows_pipe(const alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
-                             int64_t n, int c, float* scores, int bs, float* a, int64_t lda) {
+                             int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda) {
     cudaError_t e = cudaFuncSetAttribute(rows_pipe_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const int64_t tiles_total = (n + cfg.rows_per_tile - 1) / cfg.rows_per_tile;
     const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles_total));
-    rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, a, lda);
+    rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, row0, n_total, a, lda);
     return cudaGetLastError();
 }
 
 template <int MODE>
 cudaError_t launch_rows_pipe_nv(const alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
-                                int64_t n, int c, float* scores, int bs, float* a, int64_t lda) {
+                                int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda) {
     const int nv = (c / 4 + 31) / 32;
-    if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
-    if (nv <= 2) return launch_rows_pipe<2, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
-    if (nv <= 4) return launch_rows_pipe<4, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
-    if (nv <= 8) return launch_rows_pipe<8, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
-    return launch_rows_pipe<16, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, a, lda);
+    if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
+    if (nv <= 2) return launch_rows_pipe<2, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
+    if (nv <= 4) return launch_rows_pipe<4, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
+    if (nv <= 8) return launch_rows_pipe<8, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
+    return launch_rows_pipe<16, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
 }
 
 template <int NV>
@@ -495,9 +496,9 @@ extern "C" int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, i
     size_t smem = 0;
     if (vec && ld == c && n >= 4096 && ctx->greedy_variant != 1 && plan_row_pipe(ctx, c, cfg, smem)) {
         cudaError_t e;
-        if (mode == ALQ_MODE_MARGIN) e = launch_rows_pipe_nv<ALQ_MODE_MARGIN>(ctx, st, cfg, smem, logits, n, c, scores, 1, nullptr, 0);
-        else if (mode == ALQ_MODE_LEAST_CONFIDENCE) e = launch_rows_pipe_nv<ALQ_MODE_LEAST_CONFIDENCE>(ctx, st, cfg, smem, logits, n, c, scores, 1, nullptr, 0);
-        else e = launch_rows_pipe_nv<ALQ_MODE_ENTROPY>(ctx, st, cfg, smem, logits, n, c, scores, 1, nullptr, 0);
+        if (mode == ALQ_MODE_MARGIN) e = launch_rows_pipe_nv<ALQ_MODE_MARGIN>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0);
+        else if (mode == ALQ_MODE_LEAST_CONFIDENCE) e = launch_rows_pipe_nv<ALQ_MODE_LEAST_CONFIDENCE>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0);
+        else e = launch_rows_pipe_nv<ALQ_MODE_ENTROPY>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0);
         ctx->launches++;
         if (e != cudaSuccess) ALQ_FAIL(ctx, ALQ_ERR_CUDA, "rows_pipe_kernel launch failed: %s", cudaGetErrorString(e));
         return ALQ_OK;
@@ -517,11 +518,12 @@ extern "C" int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, i
 }
 
 extern "C" int alq_badge_factors(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
-                                 int32_t batch_size, float* a, int64_t lda, float* a_norm2,
-                                 void* stream) {
+                                 int32_t batch_size, int64_t row0, int64_t n_total, float* a, int64_t lda,
+                                 float* a_norm2, void* stream) {
     if (!ctx) return ALQ_ERR_INVALID;
     const int cpad = (c + 3) & ~3;
-    if (n < 0 || c <= 0 || ld < c || lda < cpad || batch_size <= 0)
+    if (n_total <= 0) { n_total = n; row0 = 0; }
+    if (n < 0 || c <= 0 || ld < c || lda < cpad || batch_size <= 0 || row0 < 0 || row0 + n > n_total)
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_badge_factors: bad shape n=%lld c=%d ld=%lld lda=%lld bs=%d",
                  (long long)n, c, (long long)ld, (long long)lda, batch_size);
     if (n == 0) return ALQ_OK;
@@ -533,20 +535,20 @@ extern "C" int alq_badge_factors(alq_ctx* ctx, const float* logits, int64_t n, i
     RowPipeCfg cfg{};
     size_t smem = 0;
     if (vec && ld == c && n >= 4096 && ctx->greedy_variant != 1 && plan_row_pipe(ctx, c, cfg, smem)) {
-        cudaError_t e = launch_rows_pipe_nv<3>(ctx, st, cfg, smem, logits, n, c, a_norm2, batch_size, a, lda);
+        cudaError_t e = launch_rows_pipe_nv<3>(ctx, st, cfg, smem, logits, n, c, a_norm2, batch_size, row0, n_total, a, lda);
         ctx->launches++;
         if (e != cudaSuccess) ALQ_FAIL(ctx, ALQ_ERR_CUDA, "rows_pipe_kernel launch failed: %s", cudaGetErrorString(e));
         return ALQ_OK;
     }
     if (vec) {
         const int nv = (c / 4 + 31) / 32;
-        if (nv <= 1) badge_factors_vec_kernel<1><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
-        else if (nv <= 2) badge_factors_vec_kernel<2><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
-        else if (nv <= 4) badge_factors_vec_kernel<4><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
-        else if (nv <= 8) badge_factors_vec_kernel<8><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
-        else badge_factors_vec_kernel<16><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda, a_norm2);
+        if (nv <= 1) badge_factors_vec_kernel<1><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, row0, n_total, a, lda, a_norm2);
+        else if (nv <= 2) badge_factors_vec_kernel<2><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, row0, n_total, a, lda, a_norm2);
+        else if (nv <= 4) badge_factors_vec_kernel<4><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, row0, n_total, a, lda, a_norm2);
+        else if (nv <= 8) badge_factors_vec_kernel<8><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, row0, n_total, a, lda, a_norm2);
+        else badge_factors_vec_kernel<16><<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, row0, n_total, a, lda, a_norm2);
     } else {
-        badge_factors_generic_kernel<<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, a, lda,
+        badge_factors_generic_kernel<<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, batch_size, row0, n_total, a, lda,
                                                                     cpad, a_norm2);
     }
     ALQ_LAUNCH_CHECK(ctx);

@@ -69,6 +69,21 @@ class Engine:
     def _check(self, rc, what):
         _lib.check(self.lib, self._h, rc, what)
 
+    def comm_init(self, process_group=None, window_bytes: int = 32 << 20):
+        """Create this rank's peer-memory window and map every peer's (CUDA IPC over NVLink).  The 64-byte
+        handles travel through torch.distributed (plumbing); afterwards the global CoreSet / k-means++ loops
+        exchange their per-step winner from inside the kernels, with no host or NCCL call per step."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        handle = (C.c_char * 64)()
+        self._check(self.lib.alq_comm_create(self._h, world, rank, int(window_bytes), handle), "alq_comm_create")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=process_group)
+        blob = b"".join(handles)
+        self._check(self.lib.alq_comm_connect(self._h, blob), "alq_comm_connect")
+        self.world, self.rank = world, rank
+        return self
+
     def set_option(self, key: str, value: int):
         """'k3_impl': 0 auto / 1 fp32 SIMT / 2 tcgen05 3xTF32;  'greedy_variant': 0 auto / 1 direct / 2 pipeline."""
         self._check(self.lib.alq_set_option(self._h, key.encode(), int(value)), "alq_set_option")
@@ -124,14 +139,15 @@ class Engine:
         return out
 
     # -- K2 ------------------------------------------------------------------------------------------
-    def badge_factors(self, logits: torch.Tensor, batch_size: int):
+    def badge_factors(self, logits: torch.Tensor, batch_size: int, row0: int = 0, n_total: int = 0):
+        """row0/n_total: this tensor is rows [row0, row0+n) of a loader pass over n_total rows (sharded pools)."""
         logits = _f32c(logits, "logits")
         n, c = logits.shape
         cpad = (c + 3) & ~3
         a = torch.empty((n, cpad), dtype=torch.float32, device=logits.device)
         an = torch.empty(n, dtype=torch.float32, device=logits.device)
         self._check(self.lib.alq_badge_factors(self._h, _ptr(logits), n, c, _ld(logits), int(batch_size),
-                                               _ptr(a), cpad, _ptr(an), self._stream()),
+                                               int(row0), int(n_total), _ptr(a), cpad, _ptr(an), self._stream()),
                     "alq_badge_factors")
         return a, an
 
@@ -189,7 +205,8 @@ class Engine:
                       uniforms: Optional[np.ndarray] = None, vpos: Optional[torch.Tensor] = None,
                       full_n: Optional[Sequence[int]] = None,
                       first_pick: Optional[Sequence[int]] = None, variant: int = 0,
-                      time_steps: bool = False):
+                      time_steps: bool = False, shard_off: Optional[Sequence[int]] = None,
+                      vpos_all: Optional[torch.Tensor] = None):
         """Runs the whole selection loop on the device; returns the picked row ids (host int32,
         partition-major, pick order) and, with time_steps, the mean streaming-kernel time in ms."""
         x = _f32c(x, "x")
@@ -227,6 +244,13 @@ class Engine:
             fp = np.ascontiguousarray(first_pick, dtype=np.int32)
             desc.first_pick_host = fp.ctypes.data
             keep.append(fp)
+        if shard_off is not None:
+            so = np.ascontiguousarray(shard_off, dtype=np.int32)
+            desc.shard_off_host = so.ctypes.data
+            keep.append(so)
+            if vpos_all is not None:
+                desc.vpos_all = vpos_all.data_ptr()
+                keep.append(vpos_all)
         desc.picks = picks.data_ptr()
         desc.variant = int(variant)
         ms = C.c_float(0.0)

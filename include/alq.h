@@ -51,6 +51,16 @@ int alq_set_option(alq_ctx* ctx, const char* key, int64_t value);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 int64_t alq_launch_count(const alq_ctx* ctx);
 
+/* ---- multi-GPU group: one process per GPU, peer-memory windows over NVLink ---------------------
+ * alq_comm_create allocates this rank's window and returns its 64-byte CUDA IPC handle; the caller
+ * exchanges the handles (e.g. torch.distributed.all_gather) and passes all of them, in rank order, to
+ * alq_comm_connect.  The global (non-partitioned) CoreSet / k-means++ loops then exchange their
+ * per-step winner through these windows from inside the kernels (alq_greedy_desc.shard_off_host).   */
+#define ALQ_IPC_HANDLE_BYTES 64
+int alq_comm_create(alq_ctx* ctx, int32_t world, int32_t rank, size_t window_bytes, void* handle_out);
+int alq_comm_connect(alq_ctx* ctx, const void* all_handles);
+int alq_comm_destroy(alq_ctx* ctx);
+
 /* ---- K1: softmax-uncertainty score -------------------------------------------------------
  * Replaces the per-batch Softmax -> topk -> subtract of margin_sampler.py:33-35 and
  * confidence_sampler.py:31-33 (entropy: SURVEY.md section 8 row A3, new).
@@ -85,9 +95,12 @@ int alq_uncertainty_query_host(alq_ctx* ctx, const float* logits_host, int64_t n
  * a_i = (softmax(z_i) - onehot(argmax z_i)) / bs_i, bs_i = size of the loader batch holding row
  * i (`batch_size`, or n % batch_size for the last short batch).  The 2048*1000-d embedding is
  * a_i (x) h_i and is never materialised.  Writes a[n, c] (columns c..lda-1 zero-filled up to the
- * next multiple of 4) and a_norm2[i] = |a_i|^2.                                               */
+ * next multiple of 4) and a_norm2[i] = |a_i|^2.
+ * A shard of a larger pool passes its offset: the rows are positions [row0, row0 + n) of a loader pass over
+ * n_total rows (n_total <= 0 means the call covers the whole pool).                               */
 int alq_badge_factors(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
-                      int32_t batch_size, float* a, int64_t lda, float* a_norm2, void* stream);
+                      int32_t batch_size, int64_t row0, int64_t n_total, float* a, int64_t lda,
+                      float* a_norm2, void* stream);
 
 /* K2p: the adaptive-pooled embedding of badge_sampler.py:41-44 (pool_h = min(16, c),
  * pool_w = 512 / pool_h) written materialised: out[i, r*pool_w + s] = pool(a_i)[r] * pool(h_i)[s]. */
@@ -152,6 +165,12 @@ typedef struct alq_greedy_desc {
     int32_t* picks;
     /* kernel variant: 0 = auto, 1 = direct-load, 2 = bulk-copy (TMA) pipeline */
     int32_t variant;
+    /* multi-GPU (needs alq_comm_create/connect; n_parts must be 1): rows [shard_off[r], shard_off[r+1])
+       of the GLOBAL candidate list live on rank r; x/a/xn/an/mind/vpos describe this rank's rows only,
+       vpos_all (device, [shard_off[world]]) is every rank's vpos concatenated, picks are global row ids
+       and identical on every rank.  NULL => single GPU. */
+    const int32_t* shard_off_host;
+    const int32_t* vpos_all;
     /* optional: device events bracketing the streaming kernel are not exposed; instead the mean
        duration of the streaming step kernel over this call is written here (ms), if non-NULL.
        Forces a stream synchronisation at the end of the call. */

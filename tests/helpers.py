@@ -98,7 +98,8 @@ class OracleEngine:
         w = np.sort(keys.numpy().view(np.uint64))[:int(b)]
         return torch.from_numpy((w & np.uint64(0xFFFFFFFF)).astype(np.int64).astype(np.int32))
 
-    def badge_factors(self, logits, batch_size):
+    def badge_factors(self, logits, batch_size, row0=0, n_total=0):
+        assert row0 == 0 and n_total in (0, logits.shape[0])
         a = O.badge_factors(logits, int(batch_size))
         cpad = (a.shape[1] + 3) & ~3
         ap = torch.zeros((a.shape[0], cpad))

@@ -222,37 +222,49 @@ def workload_config(gpus):
 # ----------------------------------------------------------------------------------------------
 # extra workloads (N = 1): CoreSet and BADGE tails at the north-star shapes
 # ----------------------------------------------------------------------------------------------
-def run_greedy_workload(eng, kind, peak, steps, warmup):
+def run_greedy_workload(eng, kind, peak, steps, warmup, world=1, rank=0):
+    """CoreSet / BADGE tail at the north-star shape.  world > 1: STRONG scaling -- the same 80 000
+    candidates are row-sharded over the ranks, the labeled set is replicated, and the per-step winner is
+    exchanged through peer-memory windows from inside the step kernels (no NCCL call in the loop)."""
+    import torch.distributed as dist
     dev = eng.device
-    g = torch.Generator(device=dev).manual_seed(1)
-    X = torch.relu(torch.randn(N_ROWS, EMB_DIM, device=dev, generator=g))
-    Y = torch.relu(torch.randn(N_LABELED, EMB_DIM, device=dev, generator=g))
+    lo, hi = rank * N_ROWS // world, (rank + 1) * N_ROWS // world
+    shard_off = [r * N_ROWS // world for r in range(world + 1)] if world > 1 else None
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    X = torch.relu(torch.randn(hi - lo, EMB_DIM, device=dev, generator=g))
+    gy = torch.Generator(device=dev).manual_seed(1)            # labeled rows: identical on every rank
+    Y = torch.relu(torch.randn(N_LABELED, EMB_DIM, device=dev, generator=gy))
     factored = kind == "badge"
     if factored:
-        lx = torch.randn(N_ROWS, N_CLASSES, device=dev, generator=g) * 3
-        ly = torch.randn(N_LABELED, N_CLASSES, device=dev, generator=g) * 3
+        lx = torch.randn(hi - lo, N_CLASSES, device=dev, generator=g) * 3
+        ly = torch.randn(N_LABELED, N_CLASSES, device=dev, generator=gy) * 3
     rng = np.random.default_rng(0)
     us = rng.random(BUDGET)
-    vpos = torch.arange(N_LABELED, N_LABELED + N_ROWS, dtype=torch.int32, device=dev)
+    vpos_all = torch.arange(N_LABELED, N_LABELED + N_ROWS, dtype=torch.int32, device=dev)
+    vpos = vpos_all[lo:hi].contiguous()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     out = {}
+    n_loc = hi - lo
 
     def one(timed):
+        if world > 1:
+            dist.barrier()
         if timed:
             ev[0].record()
         xn, yn = eng.row_norm2(X), eng.row_norm2(Y)
         XA = YA = xan = yan = None
         if factored:
-            XA, xan = eng.badge_factors(lx, 128)        # K2
-            YA, yan = eng.badge_factors(ly, 128)
+            XA, xan = eng.badge_factors(lx, 128, row0=N_LABELED + lo, n_total=N_LABELED + N_ROWS)   # K2
+            YA, yan = eng.badge_factors(ly, 128, row0=0, n_total=N_LABELED + N_ROWS)
         if timed:
             ev[1].record()
         mind = eng.min_dist(X, xn, Y, yn, XA, xan, YA, yan)   # K3
         if timed:
             ev[2].record()
-        picks, step_ms = eng.greedy_select(X, xn, mind, [0, N_ROWS], [BUDGET], a=XA, an=xan,
+        picks, step_ms = eng.greedy_select(X, xn, mind, [0, n_loc], [BUDGET], a=XA, an=xan,
                                            uniforms=us if factored else None, vpos=vpos if factored else None,
-                                           full_n=[N_ROWS + N_LABELED] if factored else None, time_steps=True)
+                                           full_n=[N_ROWS + N_LABELED] if factored else None, time_steps=True,
+                                           shard_off=shard_off, vpos_all=vpos_all if (factored and world > 1) else None)
         if timed:
             ev[3].record()
             torch.cuda.synchronize()
@@ -274,13 +286,19 @@ def run_greedy_workload(eng, kind, peak, steps, warmup):
     for k in acc:
         acc[k] /= steps
     ms = tot / steps
+    if world > 1:       # device time of the slowest rank
+        t = torch.tensor([ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"], acc["step_kernel_ms"]], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"], acc["step_kernel_ms"] = [float(v) for v in t]
     row_bytes = 4 * EMB_DIM + 12 + (4 * N_CLASSES if factored else 0)
-    achieved = N_ROWS * row_bytes / (acc["step_kernel_ms"] * 1e-3) / 1e9
-    flops = 2.0 * N_ROWS * N_LABELED * (EMB_DIM + (N_CLASSES if factored else 0))
+    achieved = n_loc * row_bytes / (acc["step_kernel_ms"] * 1e-3) / 1e9
+    flops = 2.0 * n_loc * N_LABELED * (EMB_DIM + (N_CLASSES if factored else 0))
     name = "step_pipe_kernel<factored,sample>" if factored else "step_pipe_kernel<dense,argmax>"
     return {
-        "workload": ("BADGESampler tail (configs[3] shape, global k-means++ on rank-1 factors, 1 GPU)" if factored
-                     else "CoresetSampler tail (configs[2] shape, global greedy k-center, 1 GPU)"),
+        "workload": (f"BADGESampler tail (configs[3] shape, global k-means++ on rank-1 factors, {world} GPU)" if factored
+                     else f"CoresetSampler tail (configs[2] shape, global greedy k-center, {world} GPU)"),
+        "scaling": "strong" if world > 1 else None, "rows_per_gpu": n_loc,
+        "exchange": "peer-memory windows (CUDA IPC over NVLink), in-kernel, per step" if world > 1 else None,
         "candidates": N_ROWS, "labeled": N_LABELED, "budget": BUDGET, "dim": EMB_DIM,
         "classes": N_CLASSES if factored else None,
         "value": N_ROWS / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "picks_unique": out["unique"],
@@ -422,11 +440,13 @@ def run_own(args):
                       f"(torch-CPU softmax/topk in batches of 128 + sort), {threads} threads = best of a probe "
                       f"over {cpu_budget} usable CPUs; {cpu_model()}",
             "selection_overlap_with_gpu": (float(len(np.intersect1d(cp, res.numpy())) / BUDGET) if world == 1 else None)}
-    if world == 1 and not args.no_extras:
+    if not args.no_extras:
         extras = {}
+        if world > 1:
+            eng.comm_init()
         for kind in ("coreset", "badge"):
             try:
-                extras[kind] = run_greedy_workload(eng, kind, peak, steps=args.extra_steps, warmup=1)
+                extras[kind] = run_greedy_workload(eng, kind, peak, steps=args.extra_steps, warmup=1, world=world, rank=rank)
             except Exception as exc:  # report, never hide
                 extras[kind] = {"error": repr(exc)}
             torch.cuda.empty_cache()

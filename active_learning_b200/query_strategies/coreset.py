@@ -136,6 +136,9 @@ class CoresetQuery(EngineMixin):
 
     # ---- coreset_sampler.py:107-133 / badge_sampler.py:50-78 ---------------------------------------
     def query(self, budget):
+        group = getattr(self, "_shard_group", None)
+        if group is not None and group.world_size > 1:
+            return self._query_global_sharded(budget, group)
         union = np.asarray(self.get_idxs_for_coreset(), dtype=np.int64)
         cacheable = (self.freeze_feature and not self.GRADIENT_EMBEDDING
                      and self.subset_unlabeled is None and self.subset_labeled is None)
@@ -154,6 +157,83 @@ class CoresetQuery(EngineMixin):
         first, unif = self._draw([len(union)], [len(lab_pos)], [budget])
         picks = self._select(feats, factors, [lab_pos], [cand_pos], [0], [budget], first, unif)[0]
         labeled_idxs_cur_rd = union[cand_pos[picks]].tolist()
+        return labeled_idxs_cur_rd, len(labeled_idxs_cur_rd)
+
+    # ---- the same query with the rows of the union sharded over the ranks of a ShardGroup -------------
+    def _query_global_sharded(self, budget, group):
+        """Every rank forwards rows [lo, hi) of the sorted union, keeps its unlabeled rows as candidates,
+        receives the (few) labeled rows of the other ranks, and the selection loop exchanges its per-step
+        winner through the engine's peer-memory windows.  Host bookkeeping and the RNG stream are replicated,
+        so every rank returns the same list as the single-GPU query."""
+        eng = self.get_engine()
+        union = np.asarray(self.get_idxs_for_coreset(), dtype=np.int64)
+        is_lab = self.already_labeled_idxs(boolean=True)[union]
+        budget = int(min(self.available_query_idxs(boolean=True)[union].sum(), budget))
+        if budget <= 0:
+            return [], 0
+        n_u, G, r = len(union), group.world_size, group.rank
+        bounds = [group.row_range(n_u, q) for q in range(G)]
+        lo, hi = bounds[r]
+        lab_pos, cand_pos = np.flatnonzero(is_lab), np.flatnonzero(~is_lab)
+        first, unif = self._draw([n_u], [len(lab_pos)], [budget])
+
+        self.feature_net.eval()
+        if self.GRADIENT_EMBEDDING:
+            logits, emb = self._forward_pool(union[lo:hi].tolist(), self.net, want_features=True)
+            bs = int(self.train_args["loader_te_args"]["batch_size"])
+            factors, _ = eng.badge_factors(logits, bs, row0=lo, n_total=n_u)      # 1/bs of the GLOBAL loader pass
+        else:
+            _, emb = self._forward_pool(union[lo:hi].tolist(), self.feature_net, want_features=True)
+            factors = None
+        dev = emb.device
+        my_lab = lab_pos[(lab_pos >= lo) & (lab_pos < hi)] - lo
+        my_cand = cand_pos[(cand_pos >= lo) & (cand_pos < hi)] - lo
+        lab_counts = [int(((lab_pos >= a) & (lab_pos < b)).sum()) for a, b in bounds]
+        cand_counts = [int(((cand_pos >= a) & (cand_pos < b)).sum()) for a, b in bounds]
+        shard_off = np.concatenate(([0], np.cumsum(cand_counts))).astype(np.int32)
+        X, XA = _gather(emb, my_cand, dev), _gather(factors, my_cand, dev)
+        xn = eng.row_norm2(X)
+        xan = eng.row_norm2(XA) if XA is not None else None
+        mind = torch.full((X.shape[0],), float("inf"), dtype=torch.float32, device=dev)
+        head = []
+        if len(lab_pos):
+            Y = group.all_gather_rows(_gather(emb, my_lab, dev), lab_counts)
+            YA = group.all_gather_rows(_gather(factors, my_lab, dev), lab_counts) if factors is not None else None
+        else:
+            # nothing labeled: first centre by np.random.choice (D^2) / minimax (arg-max), then it plays the
+            # role of the labeled set for the remaining budget - 1 picks (coreset_sampler.py:97-100)
+            allX = group.all_gather_rows(X, cand_counts)
+            allA = group.all_gather_rows(XA, cand_counts) if XA is not None else None
+            if self.RANDOMIZE:
+                q0 = int(first[0])
+            else:
+                alln = eng.row_norm2(allX)
+                alla = eng.row_norm2(allA) if allA is not None else None
+                far = eng.min_dist(X, xn, allX, alln, XA, xan, allA, alla, reduce_max=True)
+                far_all = group.all_gather_rows(far, cand_counts)
+                q0 = eng.argmin(far_all)
+            head = [q0]
+            Y = allX[q0:q0 + 1].contiguous()
+            YA = allA[q0:q0 + 1].contiguous() if allA is not None else None
+            if shard_off[r] <= q0 < shard_off[r + 1]:
+                pass        # excluded below, after the distance pass
+            budget -= 1
+            unif = [unif[0][1:]]
+        if Y.shape[0]:
+            eng.min_dist(X, xn, Y, eng.row_norm2(Y), XA, xan, YA, eng.row_norm2(YA) if YA is not None else None,
+                         out=mind)
+        if head and shard_off[r] <= head[0] < shard_off[r + 1]:
+            mind[head[0] - int(shard_off[r])] = float("-inf")     # the first centre is not a candidate any more
+        picks = []
+        if budget > 0:
+            vpos_all = torch.as_tensor(cand_pos.astype(np.int32), device=dev)
+            picks = eng.greedy_select(
+                X, xn, mind, [0, X.shape[0]], [budget], a=XA, an=xan,
+                uniforms=unif[0] if self.RANDOMIZE else None,
+                vpos=vpos_all[int(shard_off[r]):int(shard_off[r + 1])].contiguous() if self.RANDOMIZE else None,
+                full_n=[n_u] if self.RANDOMIZE else None, shard_off=shard_off, vpos_all=vpos_all).tolist()
+        chosen = head + picks
+        labeled_idxs_cur_rd = union[cand_pos[np.asarray(chosen, dtype=np.int64)]].tolist()
         return labeled_idxs_cur_rd, len(labeled_idxs_cur_rd)
 
 

@@ -54,6 +54,21 @@ class ShardGroup:
             return out
         return out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
 
+    # ---- variable-length row gathers (plumbing for the global CoreSet / BADGE queries) ----------------
+    def all_gather_rows(self, t, counts):
+        """Concatenate every rank's [counts[r], D] tensor in rank order.  The counts are known on every
+        rank from the (replicated) host bookkeeping, so only padded data travels."""
+        width = t.shape[1] if t.dim() == 2 else 1
+        cmax = max(int(c) for c in counts) if len(counts) else 0
+        pad = torch.zeros((cmax, width), dtype=t.dtype, device=t.device)
+        if t.numel():
+            pad[:t.shape[0]] = t.reshape(t.shape[0], width)
+        out = torch.empty((self.world_size * cmax, width), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad, group=self.pg)
+        parts = [out[r * cmax:r * cmax + int(counts[r])] for r in range(self.world_size)]
+        res = torch.cat(parts, dim=0)
+        return res if t.dim() == 2 else res.reshape(-1)
+
     # ---- partition dealing ------------------------------------------------------------------------
     def my_partitions(self, n_parts, rank=None):
         r = self.rank if rank is None else rank

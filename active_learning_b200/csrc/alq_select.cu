@@ -275,6 +275,31 @@ merge_rank_kernel(const unsigned long long* __restrict__ keys, int64_t b, int ru
     if (rank < keep) out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
 }
 
+// Every rank's B words arrive already sorted (K1b order), so the G lists are merged by rank counting
+// alone: rank = own index + sum over the other lists of #words smaller (binary search), no sorting pass.
+__global__ void __launch_bounds__(256)
+merge_sorted_lists_kernel(const unsigned long long* __restrict__ keys, int lists, int64_t len,
+                          int32_t* __restrict__ out_pos, int64_t keep) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= lists * len) return;
+    const unsigned long long key = keys[i];
+    if (key == ~0ull) return;                               // padding
+    const int mine = static_cast<int>(i / len);
+    int64_t rank = i - static_cast<int64_t>(mine) * len;
+    for (int r = 0; r < lists; ++r) {
+        if (r == mine) continue;
+        const unsigned long long* base = keys + static_cast<int64_t>(r) * len;
+        int64_t lo = 0, hi = len;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (base[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+        if (rank >= keep) return;
+    }
+    out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
+}
+
 // multi-GPU merge helpers -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 topb_pack_kernel(const float* __restrict__ scores, const int32_t* __restrict__ pos, int64_t k, int64_t row_lo,
@@ -380,13 +405,20 @@ extern "C" int alq_topb_pack(alq_ctx* ctx, const float* scores, const int32_t* p
     return ALQ_OK;
 }
 
-extern "C" int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int64_t b, int32_t* out_gpos,
-                              void* stream) {
+extern "C" int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int64_t list_len, int64_t b,
+                              int32_t* out_gpos, void* stream) {
     if (!ctx) return ALQ_ERR_INVALID;
     if (n < 0 || b < 0 || b > n || n > (1 << 24) || !keys || !out_gpos)
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_topb_merge: bad arguments (n=%lld b=%lld)", (long long)n, (long long)b);
     if (b == 0) return ALQ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (list_len > 0) {
+        if (n % list_len) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_topb_merge: n is not a multiple of list_len");
+        merge_sorted_lists_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const unsigned long long*>(keys), static_cast<int>(n / list_len), list_len, out_gpos, b);
+        ALQ_LAUNCH_CHECK(ctx);
+        return ALQ_OK;
+    }
     int rc = alq_scratch_reserve(ctx, scratch_need({static_cast<size_t>(n) * 8}));
     if (rc) return rc;
     unsigned long long* work = ScratchCursor(ctx->scratch).take<unsigned long long>(n);

@@ -119,11 +119,12 @@ class Engine:
                                            _ptr(out), self._stream()), "alq_topb_pack")
         return out
 
-    def topb_merge(self, keys: torch.Tensor, b: int) -> torch.Tensor:
-        """Global positions (int32) of the b smallest packed words, ascending."""
+    def topb_merge(self, keys: torch.Tensor, b: int, list_len: int = 0) -> torch.Tensor:
+        """Global positions (int32) of the b smallest packed words, ascending.  list_len > 0: `keys` is a
+        concatenation of individually sorted lists of that length (merge by rank counting, no sort)."""
         out = torch.empty(int(b), dtype=torch.int32, device=keys.device)
-        self._check(self.lib.alq_topb_merge(self._h, _ptr(keys), keys.numel(), int(b), _ptr(out), self._stream()),
-                    "alq_topb_merge")
+        self._check(self.lib.alq_topb_merge(self._h, _ptr(keys), keys.numel(), int(list_len), int(b), _ptr(out),
+                                            self._stream()), "alq_topb_merge")
         return out
 
     def uncertainty_query_host(self, logits_host: torch.Tensor, mode: int, b: int) -> np.ndarray:

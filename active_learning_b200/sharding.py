@@ -49,7 +49,7 @@ class ShardGroup:
         mine, allk = self._buf["mine"], self._buf["all"]
         engine.topb_pack(scores_local, pos_local, row_lo, b, out=mine)
         dist.all_gather_into_tensor(allk, mine, group=self.pg)
-        out = engine.topb_merge(allk, b)          # int32 device tensor of global positions
+        out = engine.topb_merge(allk, b, list_len=b)   # G sorted lists -> int32 global positions, on the device
         if not to_host:
             return out
         return out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF

@@ -73,6 +73,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_rows = []
 
     def __enter__(self):
         try:
@@ -88,6 +89,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+            self.t_rows.append(time.perf_counter())
+
+    def wait_first(self, timeout=8.0):
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
 
     def __exit__(self, *a):
         if self.proc:
@@ -98,9 +105,17 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, window=None):
+        """window = (t0, t1) perf_counter bounds of the timed region; samples inside it are preferred, else
+        every sample taken while this process kept the GPU busy (warm-up .. e2e) is used and said so."""
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows
+        note = "samples span warm-up..e2e (the timed region is shorter than the 100 ms sampling period)"
+        if window is not None:
+            inside = [r for r, t in zip(self.rows, self.t_rows) if window[0] <= t <= window[1]]
+            if inside:
+                rows, note = inside, "samples inside the timed region"
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -113,7 +128,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": note}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -364,6 +379,9 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    clocks.wait_first()
     for i in range(max(args.warmup, 3)):
         step(i)
     k1_pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -371,13 +389,14 @@ def run_own(args):
     sync_all()
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        sync_all()
-        e0.record()
-        for i in range(args.steps):
-            step(i, k1_pairs[i])
-        e1.record()
-        sync_all()
+    sync_all()
+    t_w0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step(i, k1_pairs[i])
+    e1.record()
+    sync_all()
+    t_w1 = time.perf_counter()
     res = host_out[(args.steps - 1) & 1].clone()
     launches = eng.launches - launches0
     ms_total = e0.elapsed_time(e1)
@@ -408,13 +427,14 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     assert np.array_equal(np.sort(hp), np.sort(eng.select_smallest(scores, BUDGET).cpu().numpy()))
+    clocks.__exit__(None, None, None)
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(world),
-        "clocks": clocks.summary(),
+        "clocks": clocks.summary((t_w0, t_w1)),
         "e2e": {"value": N_ROWS * world / e2e_s, "unit": "samples/s",
                 "h2d_bytes_per_step": N_ROWS * N_CLASSES * 4, "d2h_bytes_per_step": BUDGET * 4,
                 "ms_per_step": e2e_s * 1e3, "api": "alq_uncertainty_query_host (pinned host logits)"},

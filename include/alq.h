@@ -78,11 +78,13 @@ int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
 /* Multi-GPU top-B (rows sharded over G ranks): each rank packs its local winners as
  * out[i] = ord(scores[pos[i]]) << 32 | (row_lo + pos[i])  (i < k; padded with ~0 up to b_pad),
  * the G*b_pad words are all-gathered by the caller (NCCL), and alq_topb_merge returns the global
- * positions of the b smallest words in ascending order -- the same (score, position) order as K1b. */
+ * positions of the b smallest words in ascending order -- the same (score, position) order as K1b.
+ * list_len > 0 declares that keys is n / list_len individually sorted lists (what alq_topb_pack of
+ * K1b output produces): they are merged by rank counting, without a sorting pass.               */
 int alq_topb_pack(alq_ctx* ctx, const float* scores, const int32_t* pos, int64_t k, int64_t row_lo,
                   int64_t b_pad, uint64_t* out, void* stream);
-int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int64_t b, int32_t* out_gpos,
-                   void* stream);
+int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int64_t list_len, int64_t b,
+                   int32_t* out_gpos, void* stream);
 
 /* Same tail for HOST buffers (what a CPU-tensor caller of MarginSampler.query has): pinned or
  * pageable host logits -> chunked H2D overlapped with K1 -> K1b -> positions back on the host.

@@ -94,7 +94,7 @@ class OracleEngine:
             return out
         return t
 
-    def topb_merge(self, keys, b):
+    def topb_merge(self, keys, b, list_len=0):
         w = np.sort(keys.numpy().view(np.uint64))[:int(b)]
         return torch.from_numpy((w & np.uint64(0xFFFFFFFF)).astype(np.int64).astype(np.int32))
 

@@ -168,8 +168,9 @@ def test_topb_pack_merge_equals_global_select(eng):
         loc = scores[lo:hi].contiguous()
         pos = eng.select_smallest(loc, min(b, hi - lo))
         words.append(eng.topb_pack(loc, pos, lo, b))
-    got = eng.topb_merge(torch.cat(words), b).cpu().numpy()
-    assert np.array_equal(got, eng.select_smallest(scores, b).cpu().numpy())
+    ref = eng.select_smallest(scores, b).cpu().numpy()
+    assert np.array_equal(eng.topb_merge(torch.cat(words), b).cpu().numpy(), ref)
+    assert np.array_equal(eng.topb_merge(torch.cat(words), b, list_len=b).cpu().numpy(), ref)
 
 
 @pytest.mark.parametrize("n,c", [(5003, 1000), (4097, 2048), (9000, 64), (70001, 4), (6000, 1024)])

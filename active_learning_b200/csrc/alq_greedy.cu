@@ -601,14 +601,26 @@ __device__ __forceinline__ float leaf_sum_group(const float* a, int len, int g_l
         return res;
     }
     const int stop = len - (len & 7);
-    float r = fmaxf(a[g_lane], 0.f);                 // prob = clip(min_dist, 0) (coreset_sampler.py:84)
-    for (int i = 8; i < stop; i += 8) r += fmaxf(a[i + g_lane], 0.f);
+    // issue every load of this lane first (<= 16: a leaf has <= 128 entries), then add in NumPy's order
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (8 * j + g_lane < stop) ? __ldcg(a + 8 * j + g_lane) : 0.f;
+    float tail[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) tail[j] = (g_lane == 0 && stop + j < len) ? __ldcg(a + stop + j) : 0.f;
+    float r = fmaxf(v[0], 0.f);                      // prob = clip(min_dist, 0) (coreset_sampler.py:84)
+#pragma unroll
+    for (int j = 1; j < 16; ++j)
+        if (8 * j < stop) r += fmaxf(v[j], 0.f);
     r = r + __shfl_down_sync(gmask, r, 1, 8);   // lanes 0,2,4,6: r0+r1, r2+r3, ...
     r = r + __shfl_down_sync(gmask, r, 2, 8);   // lanes 0,4
     r = r + __shfl_down_sync(gmask, r, 4, 8);   // lane 0
     res = r;
-    if (g_lane == 0)
-        for (int i = stop; i < len; ++i) res += fmaxf(a[i], 0.f);
+    if (g_lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            if (stop + j < len) res += fmaxf(tail[j], 0.f);
+    }
     return res;
 }
 
@@ -700,14 +712,32 @@ sample_cluster_kernel(SampleArgs A) {
     const int E = per / kSampThreads;                              // multiple of 4
     const int my_lo = rank * per + threadIdx.x * E;
     double loc = 0.0;
-    for (int j = 0; j < E; j += 4) {
-        const int base = my_lo + j;
-        if (base < npad) {
-            const float4 c4 = *reinterpret_cast<const float4*>(cf + base);   // zero padded to x4
-            loc += static_cast<double>(fmaxf(c4.x, 0.f) / total32);
-            loc += static_cast<double>(fmaxf(c4.y, 0.f) / total32);
-            loc += static_cast<double>(fmaxf(c4.z, 0.f) / total32);
-            loc += static_cast<double>(fmaxf(c4.w, 0.f) / total32);
+    float4 keep[4];                                                 // this thread's slice when E <= 16
+    const bool small = E <= 16;
+    if (small) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int base = my_lo + 4 * j;
+            keep[j] = (4 * j < E && base < npad) ? __ldcg(reinterpret_cast<const float4*>(cf + base))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            loc += static_cast<double>(fmaxf(keep[j].x, 0.f) / total32);
+            loc += static_cast<double>(fmaxf(keep[j].y, 0.f) / total32);
+            loc += static_cast<double>(fmaxf(keep[j].z, 0.f) / total32);
+            loc += static_cast<double>(fmaxf(keep[j].w, 0.f) / total32);
+        }
+    } else {
+        for (int j = 0; j < E; j += 4) {
+            const int base = my_lo + j;
+            if (base < npad) {
+                const float4 c4 = *reinterpret_cast<const float4*>(cf + base);   // zero padded to x4
+                loc += static_cast<double>(fmaxf(c4.x, 0.f) / total32);
+                loc += static_cast<double>(fmaxf(c4.y, 0.f) / total32);
+                loc += static_cast<double>(fmaxf(c4.z, 0.f) / total32);
+                loc += static_cast<double>(fmaxf(c4.w, 0.f) / total32);
+            }
         }
     }
     double inc = loc;                                               // inclusive scan inside the warp
@@ -744,13 +774,28 @@ sample_cluster_kernel(SampleArgs A) {
     if (claims) {
         double run = t_base;
         int hit = -1, last_nz = -1;
-        for (int j = 0; j < E && hit < 0; ++j) {
-            const int k = my_lo + j;
-            if (k >= n) break;
-            const float c = fmaxf(cf[k], 0.f);
-            if (c > 0.f) last_nz = k;
-            run += static_cast<double>(c / total32);
-            if ((run / total) > u) hit = k;
+        if (small) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 q4 = keep[j >> 2];
+                const float raw = (j & 3) == 0 ? q4.x : (j & 3) == 1 ? q4.y : (j & 3) == 2 ? q4.z : q4.w;
+                const int k = my_lo + j;
+                if (j < E && k < n && hit < 0) {
+                    const float c = fmaxf(raw, 0.f);
+                    if (c > 0.f) last_nz = k;
+                    run += static_cast<double>(c / total32);
+                    if ((run / total) > u) hit = k;
+                }
+            }
+        } else {
+            for (int j = 0; j < E && hit < 0; ++j) {
+                const int k = my_lo + j;
+                if (k >= n) break;
+                const float c = fmaxf(cf[k], 0.f);
+                if (c > 0.f) last_nz = k;
+                run += static_cast<double>(c / total32);
+                if ((run / total) > u) hit = k;
+            }
         }
         if (hit < 0) hit = last_nz;        // fp64 re-association moved the crossing by an ulp
         atomicMax(&sh_hit, hit);

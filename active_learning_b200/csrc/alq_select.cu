@@ -230,16 +230,16 @@ sort_emit_kernel(const unsigned long long* __restrict__ keys, int64_t b, int32_t
     if (i < b) out_pos[i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
 }
 
-// B <= 64k: sort runs of 2048 keys in shared memory (one CTA each), then place every key at
+// B <= 64k: sort runs of 512 keys in shared memory (one CTA each), then place every key at
 //   rank = (index in own run) + sum over the other runs of #keys smaller than it   (keys are unique)
 // by binary search.  Two launches of a few microseconds instead of one 160 us single-CTA network.
-constexpr int kRun = 2048;
+constexpr int kRun = 512;            // keys per run; one CTA of kRun/2 threads sorts a run (45 steps)
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kRun / 2)
 sort_runs_kernel(unsigned long long* __restrict__ keys, int64_t b) {
     __shared__ unsigned long long sk[kRun];
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kRun;
-    for (int i = threadIdx.x; i < kRun; i += 1024) sk[i] = base + i < b ? keys[base + i] : ~0ull;
+    for (int i = threadIdx.x; i < kRun; i += kRun / 2) sk[i] = base + i < b ? keys[base + i] : ~0ull;
     __syncthreads();
     for (int k = 2; k <= kRun; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -249,10 +249,13 @@ sort_runs_kernel(unsigned long long* __restrict__ keys, int64_t b) {
             __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < kRun; i += 1024)
+    for (int i = threadIdx.x; i < kRun; i += kRun / 2)
         if (base + i < b) keys[base + i] = sk[i];
 }
 
+// rank = index in own run + sum over the other runs of #keys smaller.  The binary searches over the other
+// runs are independent, so they advance in lock step, 8 runs at a time: 9 dependent load rounds instead
+// of 9 * runs.
 __global__ void __launch_bounds__(256)
 merge_rank_kernel(const unsigned long long* __restrict__ keys, int64_t b, int runs,
                   int32_t* __restrict__ out_pos, int64_t keep) {
@@ -261,18 +264,33 @@ merge_rank_kernel(const unsigned long long* __restrict__ keys, int64_t b, int ru
     const unsigned long long key = keys[i];
     const int my_run = static_cast<int>(i / kRun);
     int64_t rank = i - static_cast<int64_t>(my_run) * kRun;
-    for (int r = 0; r < runs; ++r) {
-        if (r == my_run) continue;
-        const int64_t lo0 = static_cast<int64_t>(r) * kRun;
-        const int len = static_cast<int>(min(static_cast<int64_t>(kRun), b - lo0));
-        int lo = 0, hi = len;            // first index with keys[lo0 + idx] >= key
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (keys[lo0 + mid] < key) lo = mid + 1; else hi = mid;
+    constexpr int W = 8;
+    for (int r0 = 0; r0 < runs; r0 += W) {
+        int lo[W], hi[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int r = r0 + w;
+            lo[w] = 0;
+            hi[w] = (r < runs && r != my_run) ? static_cast<int>(min(static_cast<int64_t>(kRun), b - static_cast<int64_t>(r) * kRun)) : 0;
         }
-        rank += lo;
+#pragma unroll 1
+        for (int step = 0; step < 10; ++step) {      // 2^9 = kRun: at most 10 rounds
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                if (lo[w] < hi[w]) {
+                    const int mid = (lo[w] + hi[w]) >> 1;
+                    if (keys[static_cast<int64_t>(r0 + w) * kRun + mid] < key) lo[w] = mid + 1; else hi[w] = mid;
+                    any = true;
+                }
+            }
+            if (!any) break;
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) rank += lo[w];
+        if (rank >= keep) return;
     }
-    if (rank < keep) out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
+    out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
 }
 
 // Every rank's B words arrive already sorted (K1b order), so the G lists are merged by rank counting
@@ -366,7 +384,7 @@ extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n,
 
     if (b <= 65536) {
         const int runs = static_cast<int>((b + kRun - 1) / kRun);
-        sort_runs_kernel<<<runs, 1024, 0, st>>>(keys, b);
+        sort_runs_kernel<<<runs, kRun / 2, 0, st>>>(keys, b);
         ALQ_LAUNCH_CHECK(ctx);
         merge_rank_kernel<<<static_cast<int>((b + 255) / 256), 256, 0, st>>>(keys, b, runs, out_pos, b);
         ALQ_LAUNCH_CHECK(ctx);
@@ -424,7 +442,7 @@ extern "C" int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int
     unsigned long long* work = ScratchCursor(ctx->scratch).take<unsigned long long>(n);
     ALQ_CUDA(ctx, cudaMemcpyAsync(work, keys, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToDevice, st));
     const int runs = static_cast<int>((n + kRun - 1) / kRun);
-    sort_runs_kernel<<<runs, 1024, 0, st>>>(work, n);
+    sort_runs_kernel<<<runs, kRun / 2, 0, st>>>(work, n);
     ALQ_LAUNCH_CHECK(ctx);
     merge_rank_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(work, n, runs, out_gpos, b);
     ALQ_LAUNCH_CHECK(ctx);

@@ -636,9 +636,10 @@ __device__ __forceinline__ float leaf_sum_group(const float* a, int len, int g_l
 // identical values and exactly one thread claims the draw.
 __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kSampThreads, 1)
 sample_cluster_kernel(SampleArgs A) {
-    extern __shared__ float val[];                 // 2*n_leaves - 1 tree nodes
+    extern __shared__ float val[];                 // 2*n_leaves tree nodes, then the combine schedule (ints)
     __shared__ double sh_w[32];
     __shared__ int sh_hit;
+    __shared__ int s_level_off[40];
     const int p = blockIdx.x / kCL;
     const int rank = static_cast<int>(cluster_rank());
     const PartSched S = A.sched[p];
@@ -658,6 +659,17 @@ sample_cluster_kernel(SampleArgs A) {
     }
     const int* leaf_off = A.leaf_off + S.leaf_base;
     float* leafval = A.leafval + S.leaf_base;
+    // The combine schedule (3 ints per internal node) is needed only after the leaf sums: start copying it
+    // into shared memory now (cp.async, no register staging) so the tree folds without global-load latency.
+    int* s_comb = reinterpret_cast<int*>(val + 2 * K);
+    {
+        const int n_int = 3 * (K - 1);
+        const int* g_comb = A.comb + 3 * S.comb_base;
+        for (int i = threadIdx.x; i < n_int; i += kSampThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_comb + i)), "l"(g_comb + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (threadIdx.x <= S.n_levels && threadIdx.x < 40) s_level_off[threadIdx.x] = A.level_off[S.level_base + threadIdx.x];
+    }
 
     float total32 = 0.f;
     for (int attempt = 0;; ++attempt) {
@@ -676,11 +688,12 @@ sample_cluster_kernel(SampleArgs A) {
         }
         cluster_sync_all();
         for (int i = threadIdx.x; i < K; i += kSampThreads) val[i] = __ldcg(leafval + i);
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
         for (int h = 0; h < S.n_levels; ++h) {
-            const int lo = A.level_off[S.level_base + h], hi = A.level_off[S.level_base + h + 1];
+            const int lo = s_level_off[h], hi = s_level_off[h + 1];
             for (int j = lo + threadIdx.x; j < hi; j += kSampThreads) {
-                const int* cb = A.comb + 3 * (S.comb_base + j);
+                const int* cb = s_comb + 3 * j;
                 val[cb[0]] = val[cb[1]] + val[cb[2]];
             }
             __syncthreads();
@@ -1045,7 +1058,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
             level_off_all.push_back(run);
             max_nodes = std::max(max_nodes, 2 * K);
         }
-        if (static_cast<size_t>(max_nodes) * sizeof(float) > ctx->smem_optin - 16 * 1024)
+        if (static_cast<size_t>(max_nodes) * sizeof(float) * 5 / 2 > ctx->smem_optin - 16 * 1024)
             ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: partition too long for the sampling stage");
     }
 
@@ -1160,7 +1173,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         SA.cfull = d_cfull; SA.posinv = d_posinv;
         SA.leafval = d_leafval; SA.cta_part = d_cta_part; SA.uniforms = d_unif; SA.first_pick = d_first; SA.cur = d_cur;
         SA.picks = D->picks; SA.status = d_status; SA.step = A; SA.factored = factored ? 1 : 0;
-        samp_smem = static_cast<size_t>(max_nodes) * sizeof(float);
+        samp_smem = static_cast<size_t>(max_nodes) * sizeof(float) * 5 / 2 + 64;   // nodes + 3 ints per internal node
         if (samp_smem > 32 * 1024)
             ALQ_CUDA(ctx, cudaFuncSetAttribute(sample_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                static_cast<int>(samp_smem)));

@@ -230,24 +230,29 @@ sort_emit_kernel(const unsigned long long* __restrict__ keys, int64_t b, int32_t
     if (i < b) out_pos[i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
 }
 
-// B <= 64k: sort runs of 512 keys in shared memory (one CTA each), then place every key at
+// B <= 64k: sort runs of 2048 keys in shared memory (one CTA each), then place every key at
 //   rank = (index in own run) + sum over the other runs of #keys smaller than it   (keys are unique)
 // by binary search.  Two launches of a few microseconds instead of one 160 us single-CTA network.
-constexpr int kRun = 512;            // keys per run; one CTA of kRun/2 threads sorts a run (45 steps)
+constexpr int kRun = 2048;           // keys per run; one CTA of kRun/2 threads sorts a run
 
+// Bitonic network over one run in shared memory.  Thread t owns the pair (lo, lo | j); for j <= 32 all
+// pairs of a warp lie inside that warp's own 64-key chunk, so those 51 of the 66 steps need only
+// __syncwarp(); the 15 steps with j >= 64 use the block barrier.
 __global__ void __launch_bounds__(kRun / 2)
 sort_runs_kernel(unsigned long long* __restrict__ keys, int64_t b) {
     __shared__ unsigned long long sk[kRun];
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kRun;
     for (int i = threadIdx.x; i < kRun; i += kRun / 2) sk[i] = base + i < b ? keys[base + i] : ~0ull;
     __syncthreads();
+    const int t = threadIdx.x;
     for (int k = 2; k <= kRun; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const int t = threadIdx.x;
             const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
             cmpxchg(sk[lo], sk[lo | j], (lo & k) == 0);
-            __syncthreads();
+            if (j > 32) __syncthreads();          // the next step (j/2 >= 32) crosses warps
+            else __syncwarp();
         }
+        __syncthreads();                          // next k starts with j = k: crosses warps for k >= 64
     }
     for (int i = threadIdx.x; i < kRun; i += kRun / 2)
         if (base + i < b) keys[base + i] = sk[i];
@@ -274,7 +279,7 @@ merge_rank_kernel(const unsigned long long* __restrict__ keys, int64_t b, int ru
             hi[w] = (r < runs && r != my_run) ? static_cast<int>(min(static_cast<int64_t>(kRun), b - static_cast<int64_t>(r) * kRun)) : 0;
         }
 #pragma unroll 1
-        for (int step = 0; step < 10; ++step) {      // 2^9 = kRun: at most 10 rounds
+        for (int step = 0; step < 12; ++step) {      // 2^11 = kRun: at most 12 rounds
             bool any = false;
 #pragma unroll
             for (int w = 0; w < W; ++w) {

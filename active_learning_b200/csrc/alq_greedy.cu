@@ -575,6 +575,7 @@ struct SampleArgs {
     int t;
     StepArgs step;               // rows / comm description (multi-GPU: owner pushes the centre payload)
     int factored;
+    long long* dbg;              // optional phase timestamps (ALQ_SAMPLE_DEBUG=1), 8 per launch
 };
 
 constexpr int kSampThreads = 1024;
@@ -624,6 +625,13 @@ __device__ __forceinline__ float leaf_sum_group(const float* a, int len, int g_l
     return res;
 }
 
+// prob = c / S in IEEE fp32 (what NumPy computes).  Zero numerators (every labeled / picked slot) would take
+// the division's special-operand slow path: 0 / S == +0 for S > 0, so answer those without dividing.
+__device__ __forceinline__ double prob64(float raw, float total32) {
+    const float c = fmaxf(raw, 0.f);
+    return c > 0.f ? static_cast<double>(__fdiv_rn(c, total32)) : 0.0;
+}
+
 // One thread-block CLUSTER (kCL CTAs on kCL SMs) per partition.  The three dependent stages of a
 // D^2 draw -- np.sum(prob) -> prob = c / S -> inverse-CDF search -- are separated by two cluster
 // barriers instead of kernel boundaries:
@@ -634,6 +642,8 @@ __device__ __forceinline__ float leaf_sum_group(const float* a, int len, int g_l
 // Prefixes are built as ONE sequential chain (rank order, then warp order, then lane order), so the
 // "interval contains u" predicates of neighbouring CTAs / warps / threads are computed from
 // identical values and exactly one thread claims the draw.
+#define ALQ_STAMP(i) do { if (A.dbg && threadIdx.x == 0 && rank == 0) A.dbg[A.t * 8 + (i)] = clock64(); } while (0)
+
 __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(kSampThreads, 1)
 sample_cluster_kernel(SampleArgs A) {
     extern __shared__ float val[];                 // 2*n_leaves tree nodes, then the combine schedule (ints)
@@ -671,6 +681,7 @@ sample_cluster_kernel(SampleArgs A) {
         if (threadIdx.x <= S.n_levels && threadIdx.x < 40) s_level_off[threadIdx.x] = A.level_off[S.level_base + threadIdx.x];
     }
 
+    ALQ_STAMP(0);
     float total32 = 0.f;
     for (int attempt = 0;; ++attempt) {
         // ---- stage A: np.sum(prob) ---------------------------------------------------------------
@@ -686,7 +697,9 @@ sample_cluster_kernel(SampleArgs A) {
                 if (g_lane == 0) leafval[leaf] = v;
             }
         }
+        ALQ_STAMP(1);
         cluster_sync_all();
+        ALQ_STAMP(2);
         for (int i = threadIdx.x; i < K; i += kSampThreads) val[i] = __ldcg(leafval + i);
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
@@ -718,6 +731,7 @@ sample_cluster_kernel(SampleArgs A) {
         cluster_sync_all();
     }
 
+    ALQ_STAMP(3);
     // ---- stage B: np.random.choice == first k with cumsum64(p)[k] / total > u ---------------------
     const double u = A.uniforms[S.pick_off + t];
     const int npad = (n + 3) & ~3;
@@ -736,23 +750,24 @@ sample_cluster_kernel(SampleArgs A) {
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            loc += static_cast<double>(fmaxf(keep[j].x, 0.f) / total32);
-            loc += static_cast<double>(fmaxf(keep[j].y, 0.f) / total32);
-            loc += static_cast<double>(fmaxf(keep[j].z, 0.f) / total32);
-            loc += static_cast<double>(fmaxf(keep[j].w, 0.f) / total32);
+            loc += prob64(keep[j].x, total32);
+            loc += prob64(keep[j].y, total32);
+            loc += prob64(keep[j].z, total32);
+            loc += prob64(keep[j].w, total32);
         }
     } else {
         for (int j = 0; j < E; j += 4) {
             const int base = my_lo + j;
             if (base < npad) {
                 const float4 c4 = *reinterpret_cast<const float4*>(cf + base);   // zero padded to x4
-                loc += static_cast<double>(fmaxf(c4.x, 0.f) / total32);
-                loc += static_cast<double>(fmaxf(c4.y, 0.f) / total32);
-                loc += static_cast<double>(fmaxf(c4.z, 0.f) / total32);
-                loc += static_cast<double>(fmaxf(c4.w, 0.f) / total32);
+                loc += prob64(c4.x, total32);
+                loc += prob64(c4.y, total32);
+                loc += prob64(c4.z, total32);
+                loc += prob64(c4.w, total32);
             }
         }
     }
+    ALQ_STAMP(7);
     double inc = loc;                                               // inclusive scan inside the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -768,12 +783,15 @@ sample_cluster_kernel(SampleArgs A) {
         cta_total += sh_w[w];
     }
     if (threadIdx.x == 0) A.cta_part[p * kCL + rank] = cta_total;
+    ALQ_STAMP(4);
     cluster_sync_all();
+    ALQ_STAMP(5);
     double pre = 0.0, total = 0.0;                                  // ... and over CTAs
     for (int q = 0; q < kCL; ++q) {
         if (q == rank) pre = total;
         total += __ldcg(&A.cta_part[p * kCL + q]);
     }
+    ALQ_STAMP(6);
     const double cta_after = pre + cta_total;
     const bool cta_claims = !(rank > 0 && (pre / total) > u) && ((cta_after / total) > u || rank == kCL - 1);
     if (!cta_claims) return;
@@ -794,9 +812,8 @@ sample_cluster_kernel(SampleArgs A) {
                 const float raw = (j & 3) == 0 ? q4.x : (j & 3) == 1 ? q4.y : (j & 3) == 2 ? q4.z : q4.w;
                 const int k = my_lo + j;
                 if (j < E && k < n && hit < 0) {
-                    const float c = fmaxf(raw, 0.f);
-                    if (c > 0.f) last_nz = k;
-                    run += static_cast<double>(c / total32);
+                    if (raw > 0.f) last_nz = k;
+                    run += prob64(raw, total32);
                     if ((run / total) > u) hit = k;
                 }
             }
@@ -804,9 +821,9 @@ sample_cluster_kernel(SampleArgs A) {
             for (int j = 0; j < E && hit < 0; ++j) {
                 const int k = my_lo + j;
                 if (k >= n) break;
-                const float c = fmaxf(cf[k], 0.f);
-                if (c > 0.f) last_nz = k;
-                run += static_cast<double>(c / total32);
+                const float raw = cf[k];
+                if (raw > 0.f) last_nz = k;
+                run += prob64(raw, total32);
                 if ((run / total) > u) hit = k;
             }
         }
@@ -1173,6 +1190,12 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         SA.cfull = d_cfull; SA.posinv = d_posinv;
         SA.leafval = d_leafval; SA.cta_part = d_cta_part; SA.uniforms = d_unif; SA.first_pick = d_first; SA.cur = d_cur;
         SA.picks = D->picks; SA.status = d_status; SA.step = A; SA.factored = factored ? 1 : 0;
+        if (getenv("ALQ_SAMPLE_DEBUG")) {
+            static long long* dbg_buf = nullptr;
+            if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * 8 * sizeof(long long));
+            cudaMemsetAsync(dbg_buf, 0, 64 * 8 * sizeof(long long), st);
+            SA.dbg = bmax <= 64 ? dbg_buf : nullptr;
+        }
         samp_smem = static_cast<size_t>(max_nodes) * sizeof(float) * 5 / 2 + 64;   // nodes + 3 ints per internal node
         if (samp_smem > 32 * 1024)
             ALQ_CUDA(ctx, cudaFuncSetAttribute(sample_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1250,6 +1273,16 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         // the sampling variant reports a sticky numeric status; timing needs the events resolved
         ALQ_CUDA(ctx, cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
         ALQ_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (sample && SA.dbg) {
+        std::vector<long long> hd(64 * 8);
+        cudaMemcpy(hd.data(), SA.dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (int t = 0; t < std::min(bmax, 6); ++t) {
+            fprintf(stderr, "[alq sample dbg] t=%d cycles:", t);
+            for (int i = 1; i < 7; ++i) fprintf(stderr, " %lld", hd[t * 8 + i] - hd[t * 8 + i - 1]);
+            fprintf(stderr, " | stageB loads+loc %lld scan+publish %lld", hd[t * 8 + 7] - hd[t * 8 + 3], hd[t * 8 + 4] - hd[t * 8 + 7]);
+            fprintf(stderr, "\n");
+        }
     }
     if (timing) {
         double acc = 0.0;

@@ -5,6 +5,7 @@
 // Reference semantics: margin_sampler.py:33-35, confidence_sampler.py:31-33,
 // badge_sampler.py:33-44, coreset_sampler.py:61 (all under /root/reference/src/query_strategies).
 #include <initializer_list>
+#include <stdlib.h>
 
 #include "alq_common.cuh"
 
@@ -132,6 +133,7 @@ __device__ __forceinline__ float batch_scale(int64_t row, int64_t n, int bs) {
 // ---------------------------------------------------------------------------------------------
 struct RowPipeCfg {
     int rows_per_tile, stages, consumers, tile_floats;
+    int split;      // consumer warps per tile (rows of a tile are dealt round-robin to them)
 };
 
 template <int NV>
@@ -145,7 +147,7 @@ __device__ __forceinline__ void load_row_smem(const float4* p, int lane, int nve
 
 // MODE 0..2: scores; MODE 3: BADGE factors (writes a[row, :] and a_norm2[row])
 template <int NV, int MODE>
-__global__ void __launch_bounds__(32 * 17, 1)
+__global__ void __launch_bounds__(1024, 1)
 rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg cfg, float* __restrict__ scores,
                  int bs, int64_t grow0, int64_t n_total, float* __restrict__ a, int64_t lda) {
     extern __shared__ __align__(128) unsigned char smem_rows[];
@@ -159,7 +161,7 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
     const int64_t t_lo = tiles_total * blockIdx.x / gridDim.x, t_hi = tiles_total * (blockIdx.x + 1) / gridDim.x;
     const int ntiles = static_cast<int>(t_hi - t_lo);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < cfg.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < cfg.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], cfg.split); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -179,14 +181,15 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
         }
     } else {
         const int cw = warp - 1;
-        for (int i = cw; i < ntiles; i += cfg.consumers) {
+        const int team = cw / cfg.split, sub = cw % cfg.split, teams = cfg.consumers / cfg.split;
+        for (int i = team; i < ntiles; i += teams) {
             const int s = i % cfg.stages;
             const int64_t row0 = (t_lo + i) * R;
             const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
             mbar_wait(&full[s], static_cast<uint32_t>(i / cfg.stages) & 1u);
             const float* tile = tiles + static_cast<size_t>(s) * cfg.tile_floats;
             float my_score = 0.f;
-            for (int r = 0; r < rr; ++r) {
+            for (int r = sub; r < rr; r += cfg.split) {
                 float4 v[NV];
                 load_row_smem<NV>(reinterpret_cast<const float4*>(tile + static_cast<size_t>(r) * c), lane, nvec, v);
                 if (MODE < 3) {
@@ -218,8 +221,8 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);       // all smem reads of this stage are done
-            if (lane < rr) scores[row0 + lane] = my_score;
+            if (lane == 0) mbar_arrive(&empty[s]);       // this warp's smem reads of the stage are done
+            if (lane < rr && (lane % cfg.split) == sub) scores[row0 + lane] = my_score;
         }
     }
 }
@@ -433,13 +436,19 @@ int rows_grid(const alq_ctx* ctx, int64_t n, int warps_per_block) {
 bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem) {
     const size_t row_bytes = static_cast<size_t>(c) * 4;
     if (row_bytes % 16 || row_bytes > 16384 || ctx->smem_optin < 64 * 1024) return false;
-    int R = static_cast<int>(std::max<size_t>(1, 16384 / row_bytes));
+    size_t tile_target = 16384;
+    if (const char* e = getenv("ALQ_ROW_TILE_KB")) tile_target = static_cast<size_t>(std::max(1, atoi(e))) * 1024;   // tuning aid
+    int R = static_cast<int>(std::max<size_t>(1, tile_target / row_bytes));
     R = std::min(R, 32);
     const size_t tile = R * row_bytes;
     int stages = static_cast<int>((ctx->smem_optin - 4096) / tile);
     stages = std::min(stages, 16);
     if (stages < 3) return false;
-    cfg.rows_per_tile = R; cfg.stages = stages; cfg.consumers = stages; cfg.tile_floats = static_cast<int>(tile / 4);
+    int split = 2;
+    if (const char* e = getenv("ALQ_ROW_SPLIT")) split = std::max(1, std::min(4, atoi(e)));                       // tuning aid
+    while (split > 1 && (stages * split > 31 || split > R)) --split;
+    cfg.rows_per_tile = R; cfg.stages = stages; cfg.consumers = stages * split; cfg.split = split;
+    cfg.tile_floats = static_cast<int>(tile / 4);
     smem = stages * tile + 2 * stages * sizeof(uint64_t) + 128;
     return true;
 }

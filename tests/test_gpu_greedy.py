@@ -210,6 +210,22 @@ def test_greedy_exact_fixture_medium(eng, randomize, d):
         assert _run(eng, feat, ind, b, randomize=randomize, uniforms=us, variant=variant) == ref
 
 
+def test_d2_sampling_large_tree_exact(eng):
+    """Deep NumPy pairwise tree (full array of 60 000 -> 512 leaves, 9 levels, every slice of the 8-CTA
+    cluster populated) on an exact-arithmetic fixture: picks must equal the oracle's, factored and dense."""
+    rng = np.random.default_rng(77)
+    n, l0, b = 52000, 8000, 90
+    for c in (0, 8):
+        h = torch.from_numpy(rng.integers(-1, 2, size=(n + l0, 32)).astype(np.float32))
+        a = torch.from_numpy(rng.integers(-1, 2, size=(n + l0, 8)).astype(np.float32)) if c else None
+        ind = np.zeros(n + l0, dtype=bool)
+        ind[rng.choice(n + l0, l0, replace=False)] = True
+        us = rng.random(b)
+        feat = h if a is None else (a[:, :, None] * h[:, None, :]).reshape(n + l0, -1)
+        ref = O.coreset_streaming(feat, ind, b, randomize=True, uniforms=us)
+        assert _run(eng, h, ind, b, randomize=True, uniforms=us, factors=a) == ref
+
+
 def test_badge_factored_equals_materialised_reference(eng):
     """K5 on rank-1 factors == the reference's dense path on the materialised a (x) h."""
     rng = np.random.default_rng(9)

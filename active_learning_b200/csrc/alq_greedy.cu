@@ -1204,6 +1204,10 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         if (samp_smem > 32 * 1024)
             ALQ_CUDA(ctx, cudaFuncSetAttribute(sample_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                static_cast<int>(samp_smem)));
+        // alternates with the 200 KB step kernel 10 000 times: keep the same L1/shared split
+        cudaFuncSetAttribute(sample_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        cudaGetLastError();
     }
 
     // ---- t = 0 ------------------------------------------------------------------------------------------

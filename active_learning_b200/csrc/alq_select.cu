@@ -373,6 +373,21 @@ extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n,
     ALQ_CUDA(ctx, cudaMemcpyAsync(state, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     ALQ_CUDA(ctx, cudaMemsetAsync(hist, 0, kBins * sizeof(uint32_t), st));
 
+    // K1 (225 KB of dynamic shared memory) runs right before and after these small kernels: ask for the same
+    // max-shared carve-out so the SMs do not re-partition L1/shared memory at every kernel boundary.
+    static bool carve_set = false;
+    if (!carve_set) {
+        carve_set = true;
+        const int mx = cudaSharedmemCarveoutMaxShared;
+        cudaFuncSetAttribute(select_hist_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(select_hist_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(select_hist_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(select_count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(select_write_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(sort_runs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaGetLastError();
+    }
     int hgrid = static_cast<int>((n + kSelThreads * 4 - 1) / (kSelThreads * 4));
     if (hgrid > ctx->sm_count * 4) hgrid = ctx->sm_count * 4;
     if (hgrid < 1) hgrid = 1;

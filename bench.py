@@ -395,6 +395,7 @@ def run_own(args):
     for i in range(args.steps):
         step(i, k1_pairs[i])
     e1.record()
+    t_enq = time.perf_counter()
     sync_all()
     t_w1 = time.perf_counter()
     res = host_out[(args.steps - 1) & 1].clone()
@@ -439,7 +440,8 @@ def run_own(args):
                 "h2d_bytes_per_step": N_ROWS * N_CLASSES * 4, "d2h_bytes_per_step": BUDGET * 4,
                 "ms_per_step": e2e_s * 1e3, "api": "alq_uncertainty_query_host (pinned host logits)"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "score_rows_vec_kernel<8,margin> (K1)", "bound": "hbm",
+        "host_enqueue_ms_per_step": (t_enq - t_w0) * 1e3 / args.steps,
+        "roofline": {"kernel": "rows_pipe_kernel<8,margin> (K1: TMA bulk-copy pipelined softmax-margin score)", "bound": "hbm",
                      "achieved": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9 / peak,
                      "traffic": ncu_traffic("score_margin"), "kernel_ms": k1_ms, "peak_source": peak_src,

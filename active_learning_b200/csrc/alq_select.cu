@@ -345,6 +345,9 @@ int64_t next_pow2(int64_t v) {
 
 }  // namespace
 
+int alq_select_smallest_cluster(alq_ctx* ctx, const float* scores, int64_t n, int64_t b, int32_t* out_pos,
+                                cudaStream_t st);
+
 extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
                                    int32_t* out_pos, void* stream) {
     if (!ctx) return ALQ_ERR_INVALID;
@@ -354,6 +357,11 @@ extern "C" int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n,
     if (b == 0) return ALQ_OK;
     if (!scores || !out_pos) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_select_smallest: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ctx->select_impl != 1) {      // one cluster-resident launch when the pool fits (n <= 262 144, b <= 16 384)
+        const int rc = alq_select_smallest_cluster(ctx, scores, n, b, out_pos, st);
+        if (rc != ALQ_ERR_STATE) return rc;
+        if (ctx->select_impl == 2) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_select_smallest: select_impl=2 needs n <= 262144 and b <= 16384");
+    }
     const int nblocks = static_cast<int>((n + kSelChunk - 1) / kSelChunk);
     const int64_t npad = next_pow2(b < 2 ? 2 : b);
     const size_t need = scratch_need({sizeof(SelState), kBins * sizeof(uint32_t),

@@ -46,7 +46,8 @@ void alq_destroy(alq_ctx* ctx);
 const char* alq_last_error(const alq_ctx* ctx);
 /* Implementation knobs (defaults pick the fastest valid kernel):
  *   "k3_impl"        0 auto | 1 exact-fp32 SIMT contraction | 2 tcgen05 3xTF32 contraction
- *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline            */
+ *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline
+ *   "select_impl"    0 auto | 1 multi-kernel radix select   | 2 single cluster-resident launch       */
 int alq_set_option(alq_ctx* ctx, const char* key, int64_t value);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 int64_t alq_launch_count(const alq_ctx* ctx);

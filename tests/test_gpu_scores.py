@@ -62,6 +62,21 @@ def test_select_smallest_is_stable_sort_prefix(eng, n, b):
     assert np.array_equal(got, O.select_smallest(scores, b))
 
 
+@pytest.mark.parametrize("n,b", [(1, 1), (37, 37), (4097, 1365), (80000, 10000), (100000, 16384), (262144, 5000)])
+def test_select_cluster_and_multikernel_paths_agree(eng, n, b):
+    """Both K1b implementations (one cluster-resident launch / multi-kernel radix select) against the oracle,
+    on tie-heavy scores."""
+    rng = np.random.default_rng(n * 3 + b)
+    scores = torch.from_numpy((rng.integers(0, max(2, n // 40), size=n) / 32.0 - 1.0).astype(np.float32))
+    ref = O.select_smallest(scores, b)
+    try:
+        for impl in (1, 2):
+            eng.set_option("select_impl", impl)
+            assert np.array_equal(eng.select_smallest(scores.cuda(), b).cpu().numpy(), ref), impl
+    finally:
+        eng.set_option("select_impl", 0)
+
+
 def test_select_all_equal_scores(eng):
     scores = torch.full((50000,), 0.25)
     got = eng.select_smallest(scores.cuda(), 777).cpu().numpy()

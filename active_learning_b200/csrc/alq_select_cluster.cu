@@ -11,8 +11,10 @@
 //   4    per-CTA counts of {key < T} and {key == T} -> barrier -> exclusive offsets;
 //   5    compaction of the B winners as 64-bit words (key << 32 | position); ties with T are taken in
 //        position order by one warp walking the slice with ballots;
-//   6    CTAs sort runs of 2048 words (bitonic, shared memory) -> barrier;
-//   7    every CTA pulls all runs into shared memory and places its share of the words by rank counting.
+//   6    every CTA rank-sorts its share (B/8 words) in shared memory by all-pairs counting -> barrier;
+//   7    every CTA pulls all sorted shares into shared memory and places its own words by binary searches.
+#include <stdlib.h>
+
 #include "alq_common.cuh"
 
 namespace selc {
@@ -21,14 +23,16 @@ constexpr int CL = 8;
 constexpr int THREADS = 1024;
 constexpr int MAX_SLICE = 32768;          // keys per CTA
 constexpr int BINS = 2048;
-constexpr int RUN = 2048;
 constexpr int MAX_B = 16384;
 
 struct Scratch {
     uint32_t* hist_part;        // [3][CL][BINS]
     uint32_t* counts;           // [CL][2]  (lt, eq)
-    unsigned long long* words;  // [MAX_B]
+    unsigned long long* words;  // [MAX_B]      winners, unordered
+    unsigned long long* sorted; // [MAX_B + 2]  per-CTA sorted shares
+    long long* dbg;             // optional phase stamps (ALQ_SELECT_DEBUG)
 };
+#define SELC_STAMP(i) do { if (S.dbg && threadIdx.x == 0 && rank == 0) S.dbg[i] = clock64(); } while (0)
 
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -40,67 +44,59 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 }
 __device__ __forceinline__ uint32_t score_key(float s) { return alq_ord(s + 0.0f); }
 
-// histogram add with intra-warp aggregation: lanes hitting the same bin issue one shared atomic
-__device__ __forceinline__ void hist_add(uint32_t* hist, bool active, uint32_t bin) {
-    const unsigned act = __ballot_sync(0xffffffffu, active);
-    if (!active) return;
-    const unsigned peers = __match_any_sync(act, bin);
-    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
-}
-
-__device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long long& b, bool up) {
-    if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
-}
-
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 select_cluster_kernel(const float* __restrict__ scores, int n, int b, Scratch S, int32_t* __restrict__ out_pos) {
     extern __shared__ __align__(16) unsigned char smem_sel[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem_sel);                       // [slice]  (later: all runs)
     __shared__ uint32_t hist[BINS];
     __shared__ unsigned long long part[THREADS / 32];
-    __shared__ uint32_t sh_prefix, sh_lt_cursor;
+    __shared__ uint32_t sh_prefix;
     __shared__ unsigned long long sh_k;
-    __shared__ uint32_t sh_cnt[2];
+    __shared__ uint32_t w_lt[THREADS / 32], w_eq[THREADS / 32];
     const int rank = static_cast<int>(cluster_rank());
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = ((n + CL - 1) / CL + 3) & ~3;
     const int lo = rank * per, hi = min(n, lo + per);
     const int cnt = max(0, hi - lo);
 
-    // ---- stage 0: slice -> keys in shared memory ---------------------------------------------------------
-    for (int i = threadIdx.x; i < cnt; i += THREADS) keys[i] = score_key(scores[lo + i]);
+    SELC_STAMP(0);
+    // ---- stage 0: slice -> keys in shared memory, level-0 histogram on the way -------------------------------
+    for (int i = threadIdx.x; i < BINS; i += THREADS) hist[i] = 0;
     if (threadIdx.x == 0) { sh_prefix = 0; sh_k = static_cast<unsigned long long>(b); }
     __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+        const uint32_t key = score_key(scores[lo + i]);
+        keys[i] = key;
+        atomicAdd(&hist[key >> 21], 1u);
+    }
+    __syncthreads();
 
+    SELC_STAMP(1);
     // ---- stages 1-3: radix levels ---------------------------------------------------------------------------
 #pragma unroll 1
     for (int level = 0; level < 3; ++level) {
-        for (int i = threadIdx.x; i < BINS; i += THREADS) hist[i] = 0;
-        __syncthreads();
         const uint32_t prefix = sh_prefix;
-        const int iters = (cnt + THREADS - 1) / THREADS;
-        for (int it = 0; it < iters; ++it) {
-            const int i = it * THREADS + threadIdx.x;
-            const uint32_t key = i < cnt ? keys[i] : 0u;
-            bool act = i < cnt;
-            uint32_t bin;
-            if (level == 0) bin = key >> 21;
-            else if (level == 1) { act = act && (key >> 21) == prefix; bin = (key >> 10) & 0x7ffu; }
-            else { act = act && (key >> 10) == prefix; bin = key & 0x3ffu; }
-            hist_add(hist, act, bin);
+        if (level > 0) {
+            for (int i = threadIdx.x; i < BINS; i += THREADS) hist[i] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < cnt; i += THREADS) {
+                const uint32_t key = keys[i];
+                if (level == 1) { if ((key >> 21) == prefix) atomicAdd(&hist[(key >> 10) & 0x7ffu], 1u); }
+                else { if ((key >> 10) == prefix) atomicAdd(&hist[key & 0x3ffu], 1u); }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         uint32_t* mine = S.hist_part + (static_cast<size_t>(level) * CL + rank) * BINS;
         for (int i = threadIdx.x; i < BINS; i += THREADS) mine[i] = hist[i];
         cluster_sync_all();
-        // every CTA reduces the CL partial histograms itself: 2 bins per thread
+        // every CTA reduces the CL partial histograms itself: 2 bins per thread (one 8-byte load per partial)
         unsigned long long c0 = 0, c1 = 0;
-        for (int q = 0; q < CL; ++q) {
-            const uint32_t* hp = S.hist_part + (static_cast<size_t>(level) * CL + q) * BINS;
-            c0 += __ldcg(hp + 2 * threadIdx.x);
-            c1 += __ldcg(hp + 2 * threadIdx.x + 1);
-        }
-        // block inclusive scan of (c0 + c1)
+        uint2 pv[CL];
+#pragma unroll
+        for (int q = 0; q < CL; ++q)
+            pv[q] = __ldcg(reinterpret_cast<const uint2*>(S.hist_part + (static_cast<size_t>(level) * CL + q) * BINS) + threadIdx.x);
+#pragma unroll
+        for (int q = 0; q < CL; ++q) { c0 += pv[q].x; c1 += pv[q].y; }
         unsigned long long inc = c0 + c1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -122,13 +118,17 @@ select_cluster_kernel(const float* __restrict__ scores, int n, int b, Scratch S,
         }
         __syncthreads();
     }
+    SELC_STAMP(2);
     const uint32_t T = sh_prefix;
     const unsigned long long ties = sh_k;                       // how many keys equal to T are inside the budget
     const unsigned long long n_less = static_cast<unsigned long long>(b) - ties;
 
-    // ---- stage 4: counts and offsets ----------------------------------------------------------------------------
+    // ---- stage 4: counts and offsets.  Warp w owns the contiguous chunk [w*chunk, (w+1)*chunk) of the slice, so
+    //      "ties by position" is an exclusive prefix over (CTA, warp, ballot lane) ----------------------------------
+    const int chunk = ((cnt + 31) / 32 + 31) & ~31;
+    const int c_lo = min(cnt, warp * chunk), c_hi = min(cnt, c_lo + chunk);
     uint32_t lt = 0, eq = 0;
-    for (int i = threadIdx.x; i < cnt; i += THREADS) {
+    for (int i = c_lo + lane; i < c_hi; i += 32) {
         const uint32_t key = keys[i];
         lt += key < T;
         eq += key == T;
@@ -138,11 +138,15 @@ select_cluster_kernel(const float* __restrict__ scores, int n, int b, Scratch S,
         lt += __shfl_xor_sync(0xffffffffu, lt, o);
         eq += __shfl_xor_sync(0xffffffffu, eq, o);
     }
-    if (threadIdx.x < 2) sh_cnt[threadIdx.x] = 0;
+    if (lane == 0) { w_lt[warp] = lt; w_eq[warp] = eq; }
     __syncthreads();
-    if (lane == 0) { atomicAdd(&sh_cnt[0], lt); atomicAdd(&sh_cnt[1], eq); }
-    __syncthreads();
-    if (threadIdx.x < 2) S.counts[rank * 2 + threadIdx.x] = sh_cnt[threadIdx.x];
+    uint32_t lt_before = 0, eq_before = 0, lt_cta = 0, eq_cta = 0;
+    for (int w = 0; w < THREADS / 32; ++w) {
+        if (w == warp) { lt_before = lt_cta; eq_before = eq_cta; }
+        lt_cta += w_lt[w];
+        eq_cta += w_eq[w];
+    }
+    if (threadIdx.x == 0) { S.counts[rank * 2] = lt_cta; S.counts[rank * 2 + 1] = eq_cta; }
     cluster_sync_all();
     uint32_t lt_off = 0, eq_off = 0;
     for (int q = 0; q < rank; ++q) {
@@ -150,79 +154,72 @@ select_cluster_kernel(const float* __restrict__ scores, int n, int b, Scratch S,
         eq_off += __ldcg(&S.counts[q * 2 + 1]);
     }
 
-    // ---- stage 5: compaction ---------------------------------------------------------------------------------------
-    if (threadIdx.x == 0) sh_lt_cursor = 0;
-    __syncthreads();
-    if (warp == 0) {
-        // ties: the first `ties` keys equal to T by global position; this CTA's share starts at rank eq_off
-        unsigned long long rk = eq_off;
-        for (int i0 = 0; i0 < cnt && rk < ties; i0 += 32) {
+    SELC_STAMP(3);
+    // ---- stage 5: compaction of the B winners as (key << 32 | position) words ------------------------------------
+    {
+        uint32_t lt_run = lt_off + lt_before;
+        unsigned long long eq_run = static_cast<unsigned long long>(eq_off) + eq_before;
+        for (int i0 = c_lo; i0 < c_hi; i0 += 32) {
             const int i = i0 + lane;
-            const bool is = i < cnt && keys[i] == T;
-            const unsigned m = __ballot_sync(0xffffffffu, is);
-            if (is) {
-                const unsigned long long r = rk + __popc(m & ((1u << lane) - 1u));
-                if (r < ties) S.words[n_less + r] = (static_cast<unsigned long long>(T) << 32) | static_cast<uint32_t>(lo + i);
+            const uint32_t key = i < c_hi ? keys[i] : 0xffffffffu;
+            const bool is_lt = i < c_hi && key < T, is_eq = i < c_hi && key == T;
+            const unsigned m_lt = __ballot_sync(0xffffffffu, is_lt), m_eq = __ballot_sync(0xffffffffu, is_eq);
+            const unsigned below = (1u << lane) - 1u;
+            const unsigned long long word = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(lo + i);
+            if (is_lt) S.words[lt_run + __popc(m_lt & below)] = word;
+            if (is_eq) {
+                const unsigned long long r = eq_run + __popc(m_eq & below);
+                if (r < ties) S.words[n_less + r] = word;
             }
-            rk += __popc(m);
-        }
-    } else {
-        // keys below T: any order (they are sorted afterwards); slots from a block cursor, warp-aggregated
-        for (int i0 = (warp - 1) * 32; i0 < cnt; i0 += (THREADS / 32 - 1) * 32) {
-            const int i = i0 + lane;
-            const uint32_t key = i < cnt ? keys[i] : 0xffffffffu;
-            const bool is = i < cnt && key < T;
-            const unsigned m = __ballot_sync(0xffffffffu, is);
-            uint32_t base = 0;
-            if (lane == 0 && m) base = atomicAdd(&sh_lt_cursor, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (is)
-                S.words[lt_off + base + __popc(m & ((1u << lane) - 1u))] =
-                    (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(lo + i);
+            lt_run += __popc(m_lt);
+            eq_run += __popc(m_eq);
         }
     }
     cluster_sync_all();
 
-    // ---- stage 6: sort runs of RUN words ------------------------------------------------------------------------------
+    SELC_STAMP(4);
+    // ---- stage 6: every CTA rank-sorts its share of the words (<= MAX_B / CL = 2048) in shared memory: with
+    //      1024 threads an all-pairs count (broadcast reads) is ~10x faster than a 66-step bitonic network -----
     unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_sel);      // the key slice is no longer needed
-    const int runs = (b + RUN - 1) / RUN;
-    for (int run = rank; run < runs; run += CL) {
-        const int base = run * RUN;
-        for (int i = threadIdx.x; i < RUN; i += THREADS) sk[i] = base + i < b ? __ldcg(&S.words[base + i]) : ~0ull;
-        __syncthreads();
-        const int t = threadIdx.x;
-        for (int k = 2; k <= RUN; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                const int l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                cmpxchg(sk[l], sk[l | j], (l & k) == 0);
-                __syncthreads();
-            }
-        }
-        for (int i = threadIdx.x; i < RUN; i += THREADS)
-            if (base + i < b) S.words[base + i] = sk[i];
-        __syncthreads();
+    const int share = (b + CL - 1) / CL;
+    const int s_lo = min(b, rank * share), s_hi = min(b, s_lo + share), s_cnt = s_hi - s_lo;
+    for (int i = threadIdx.x; i < s_cnt; i += THREADS) sk[i] = __ldcg(&S.words[s_lo + i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < s_cnt; i += THREADS) {
+        const unsigned long long key = sk[i];
+        int rk = 0;
+#pragma unroll 8
+        for (int j = 0; j < s_cnt; ++j) rk += sk[j] < key;
+        S.sorted[s_lo + rk] = key;
     }
     cluster_sync_all();
 
-    // ---- stage 7: all runs into shared memory, place this CTA's share by rank counting ----------------------------------
-    for (int i = threadIdx.x; i < b; i += THREADS) sk[i] = __ldcg(&S.words[i]);
+    SELC_STAMP(5);
+    // ---- stage 7: all sorted shares into shared memory, place this CTA's share by rank counting -------------------
+    {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(S.sorted);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(sk);
+        const int pairs = (b + 1) >> 1;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < pairs; i += THREADS) dst[i] = __ldcg(src + i);
+    }
     __syncthreads();
-    for (int i = rank * THREADS + threadIdx.x; i < b; i += CL * THREADS) {
+    for (int i = s_lo + threadIdx.x; i < s_hi; i += THREADS) {
         const unsigned long long key = sk[i];
-        const int my_run = i / RUN;
-        int rk = i - my_run * RUN;
-        for (int r = 0; r < runs; ++r) {
-            if (r == my_run) continue;
-            const int len = min(RUN, b - r * RUN);
+        int rk = i - s_lo;
+        for (int r = 0; r < CL; ++r) {
+            if (r == rank) continue;
+            const int r_lo = min(b, r * share), len = min(b, r_lo + share) - r_lo;
             int l = 0, h = len;
             while (l < h) {
                 const int mid = (l + h) >> 1;
-                if (sk[r * RUN + mid] < key) l = mid + 1; else h = mid;
+                if (sk[r_lo + mid] < key) l = mid + 1; else h = mid;
             }
             rk += l;
         }
         out_pos[rk] = static_cast<int32_t>(key & 0xffffffffu);
     }
+    SELC_STAMP(6);
 }
 
 }  // namespace selc
@@ -233,15 +230,23 @@ int alq_select_smallest_cluster(alq_ctx* ctx, const float* scores, int64_t n, in
     using namespace selc;
     if (n > static_cast<int64_t>(CL) * MAX_SLICE || b > MAX_B || n < 1 || b < 1) return ALQ_ERR_STATE;
     const size_t hist_bytes = static_cast<size_t>(3) * CL * BINS * sizeof(uint32_t);
-    int rc = alq_scratch_reserve(ctx, scratch_need({hist_bytes, CL * 2 * sizeof(uint32_t), MAX_B * sizeof(unsigned long long)}));
+    int rc = alq_scratch_reserve(ctx, scratch_need({hist_bytes, CL * 2 * sizeof(uint32_t), MAX_B * sizeof(unsigned long long),
+                                                    (MAX_B + 2) * sizeof(unsigned long long)}));
     if (rc) return rc;
     ScratchCursor cur(ctx->scratch);
     Scratch S;
     S.hist_part = cur.take<uint32_t>(3 * CL * BINS);
     S.counts = cur.take<uint32_t>(CL * 2);
     S.words = cur.take<unsigned long long>(MAX_B);
+    S.sorted = cur.take<unsigned long long>(MAX_B + 2);
+    S.dbg = nullptr;
+    static long long* dbg_buf = nullptr;
+    if (getenv("ALQ_SELECT_DEBUG")) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
+        S.dbg = dbg_buf;
+    }
     const int per = ((static_cast<int>(n) + CL - 1) / CL + 3) & ~3;
-    size_t smem = std::max<size_t>(static_cast<size_t>(per) * 4, std::max<size_t>(static_cast<size_t>(b) * 8, RUN * 8)) + 64;
+    size_t smem = std::max<size_t>(static_cast<size_t>(per) * 4, static_cast<size_t>(b + 2) * 8) + 64;
     if (smem > ctx->smem_optin - 24 * 1024) return ALQ_ERR_STATE;
     static size_t attr_set = 0;
     if (smem > attr_set) {
@@ -250,5 +255,12 @@ int alq_select_smallest_cluster(alq_ctx* ctx, const float* scores, int64_t n, in
     }
     select_cluster_kernel<<<CL, THREADS, smem, st>>>(scores, static_cast<int>(n), static_cast<int>(b), S, out_pos);
     ALQ_LAUNCH_CHECK(ctx);
+    if (S.dbg) {
+        long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, S.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[alq select dbg] load %lld levels %lld counts %lld compact %lld sort %lld merge %lld\n", h[1] - h[0],
+                h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+    }
     return ALQ_OK;
 }

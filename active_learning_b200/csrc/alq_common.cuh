@@ -208,4 +208,54 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 
+// ---- block-wide bitonic sort of `n` (power of two, >= 64, n/2 <= blockDim.x threads used... see below) -------
+// 64-bit keys ascending, data in shared memory `sk` on entry and exit.  Thread t owns elements (2t, 2t+1):
+// every compare-exchange at distance j <= 32 happens in registers / warp shuffles (partner element i ^ j lives in
+// lane (t ^ j/2) of the same warp), so only the distances >= 64 touch shared memory and need a block barrier:
+// for n = 2048 that is 15 of the 66 steps.  All threads of the block must call it; threads with 2t >= n idle.
+__device__ __forceinline__ void alq_cx_keep(unsigned long long& mine, unsigned long long other, bool keep_min) {
+    const bool take = keep_min ? (other < mine) : (other > mine);
+    if (take) mine = other;
+}
+__device__ __forceinline__ void alq_bitonic_reg_phase(unsigned long long& e0, unsigned long long& e1, int t, int k, int j_start) {
+    // distances j_start, j_start/2, ..., 2 through shuffles, then distance 1 inside the thread
+    const bool up = ((2 * t) & k) == 0;
+    for (int j = j_start; j >= 2; j >>= 1) {
+        const bool lower = ((2 * t) & j) == 0;
+        const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, e0, j >> 1);
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, e1, j >> 1);
+        alq_cx_keep(e0, o0, lower == up);
+        alq_cx_keep(e1, o1, lower == up);
+    }
+    if ((e0 > e1) == up) { const unsigned long long x = e0; e0 = e1; e1 = x; }
+}
+__device__ __forceinline__ void alq_bitonic_sort_smem(unsigned long long* sk, int n) {
+    const int t = threadIdx.x;
+    const bool mine = 2 * t < n;                 // warps are either fully in or fully out (n >= 64)
+    unsigned long long e0 = 0, e1 = 0;
+    if (mine) { e0 = sk[2 * t]; e1 = sk[2 * t + 1]; }
+    // stages k = 2 .. 64: every distance stays inside a warp
+    if (mine) {
+        for (int k = 2; k <= 64 && k <= n; k <<= 1) alq_bitonic_reg_phase(e0, e1, t, k, k >> 1);
+        sk[2 * t] = e0; sk[2 * t + 1] = e1;
+    }
+    __syncthreads();
+    for (int k = 128; k <= n; k <<= 1) {
+        for (int j = k >> 1; j >= 64; j >>= 1) {        // block-wide distances: pair (l, l | j) per thread
+            if (mine) {
+                const int l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const unsigned long long x = sk[l], y = sk[l | j];
+                if ((x > y) == ((l & k) == 0)) { sk[l] = y; sk[l | j] = x; }
+            }
+            __syncthreads();
+        }
+        if (mine) {
+            e0 = sk[2 * t]; e1 = sk[2 * t + 1];
+            alq_bitonic_reg_phase(e0, e1, t, k, 32);
+            sk[2 * t] = e0; sk[2 * t + 1] = e1;
+        }
+        __syncthreads();
+    }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

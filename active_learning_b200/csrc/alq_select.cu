@@ -244,16 +244,7 @@ sort_runs_kernel(unsigned long long* __restrict__ keys, int64_t b) {
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kRun;
     for (int i = threadIdx.x; i < kRun; i += kRun / 2) sk[i] = base + i < b ? keys[base + i] : ~0ull;
     __syncthreads();
-    const int t = threadIdx.x;
-    for (int k = 2; k <= kRun; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-            cmpxchg(sk[lo], sk[lo | j], (lo & k) == 0);
-            if (j > 32) __syncthreads();          // the next step (j/2 >= 32) crosses warps
-            else __syncwarp();
-        }
-        __syncthreads();                          // next k starts with j = k: crosses warps for k >= 64
-    }
+    alq_bitonic_sort_smem(sk, kRun);
     for (int i = threadIdx.x; i < kRun; i += kRun / 2)
         if (base + i < b) keys[base + i] = sk[i];
 }

@@ -11,7 +11,7 @@
 //   4    per-CTA counts of {key < T} and {key == T} -> barrier -> exclusive offsets;
 //   5    compaction of the B winners as 64-bit words (key << 32 | position); ties with T are taken in
 //        position order by one warp walking the slice with ballots;
-//   6    every CTA rank-sorts its share (B/8 words) in shared memory by all-pairs counting -> barrier;
+//   6    every CTA sorts its share (B/8 words) in shared memory (bitonic network) -> barrier;
 //   7    every CTA pulls all sorted shares into shared memory and places its own words by binary searches.
 #include <stdlib.h>
 
@@ -53,6 +53,7 @@ select_cluster_kernel(const float* __restrict__ scores, int n, int b, Scratch S,
     __shared__ uint32_t sh_prefix;
     __shared__ unsigned long long sh_k;
     __shared__ uint32_t w_lt[THREADS / 32], w_eq[THREADS / 32];
+    __shared__ __align__(8) uint64_t sh_bar;
     const int rank = static_cast<int>(cluster_rank());
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = ((n + CL - 1) / CL + 3) & ~3;
@@ -178,45 +179,58 @@ select_cluster_kernel(const float* __restrict__ scores, int n, int b, Scratch S,
     cluster_sync_all();
 
     SELC_STAMP(4);
-    // ---- stage 6: every CTA rank-sorts its share of the words (<= MAX_B / CL = 2048) in shared memory: with
-    //      1024 threads an all-pairs count (broadcast reads) is ~10x faster than a 66-step bitonic network -----
+    // ---- stage 6: every CTA sorts its share of the words (<= MAX_B / CL = 2048, padded with ~0) with a bitonic
+    //      network in shared memory (an all-pairs rank count was measured 3x slower: 79k vs 27k cycles) ---------
     unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_sel);      // the key slice is no longer needed
     const int share = (b + CL - 1) / CL;
     const int s_lo = min(b, rank * share), s_hi = min(b, s_lo + share), s_cnt = s_hi - s_lo;
-    for (int i = threadIdx.x; i < s_cnt; i += THREADS) sk[i] = __ldcg(&S.words[s_lo + i]);
+    int npad = 64;
+    while (npad < share) npad <<= 1;                         // same in every CTA; <= 2048 = 2 * THREADS
+    for (int i = threadIdx.x; i < npad; i += THREADS) sk[i] = i < s_cnt ? __ldcg(&S.words[s_lo + i]) : ~0ull;
     __syncthreads();
-    for (int i = threadIdx.x; i < s_cnt; i += THREADS) {
-        const unsigned long long key = sk[i];
-        int rk = 0;
-#pragma unroll 8
-        for (int j = 0; j < s_cnt; ++j) rk += sk[j] < key;
-        S.sorted[s_lo + rk] = key;
-    }
+    alq_bitonic_sort_smem(sk, npad);
+    for (int i = threadIdx.x; i < s_cnt; i += THREADS) S.sorted[s_lo + i] = sk[i];
     cluster_sync_all();
 
     SELC_STAMP(5);
     // ---- stage 7: all sorted shares into shared memory, place this CTA's share by rank counting -------------------
     {
-        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(S.sorted);
-        ulonglong2* dst = reinterpret_cast<ulonglong2*>(sk);
-        const int pairs = (b + 1) >> 1;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < pairs; i += THREADS) dst[i] = __ldcg(src + i);
+        // one TMA bulk copy per CTA brings all sorted shares (<= 128 KB) into shared memory
+        if (threadIdx.x == 0) {
+            mbar_init(&sh_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(((b + 1) & ~1) * 8);
+            mbar_expect_tx(&sh_bar, bytes);
+            bulk_g2s(sk, S.sorted, bytes, &sh_bar);
+        }
+        mbar_wait(&sh_bar, 0);
     }
-    __syncthreads();
     for (int i = s_lo + threadIdx.x; i < s_hi; i += THREADS) {
         const unsigned long long key = sk[i];
         int rk = i - s_lo;
+        // the searches in the other CL-1 shares are independent: advance them in lock step (12 rounds)
+        int l[CL], h[CL], base[CL];
+#pragma unroll
         for (int r = 0; r < CL; ++r) {
-            if (r == rank) continue;
-            const int r_lo = min(b, r * share), len = min(b, r_lo + share) - r_lo;
-            int l = 0, h = len;
-            while (l < h) {
-                const int mid = (l + h) >> 1;
-                if (sk[r_lo + mid] < key) l = mid + 1; else h = mid;
-            }
-            rk += l;
+            base[r] = min(b, r * share);
+            l[r] = 0;
+            h[r] = r == rank ? 0 : min(b, base[r] + share) - base[r];
         }
+#pragma unroll 1
+        for (int step = 0; step < 12; ++step) {
+#pragma unroll
+            for (int r = 0; r < CL; ++r) {
+                if (l[r] < h[r]) {
+                    const int mid = (l[r] + h[r]) >> 1;
+                    if (sk[base[r] + mid] < key) l[r] = mid + 1; else h[r] = mid;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < CL; ++r) rk += l[r];
         out_pos[rk] = static_cast<int32_t>(key & 0xffffffffu);
     }
     SELC_STAMP(6);
@@ -246,7 +260,7 @@ int alq_select_smallest_cluster(alq_ctx* ctx, const float* scores, int64_t n, in
         S.dbg = dbg_buf;
     }
     const int per = ((static_cast<int>(n) + CL - 1) / CL + 3) & ~3;
-    size_t smem = std::max<size_t>(static_cast<size_t>(per) * 4, static_cast<size_t>(b + 2) * 8) + 64;
+    size_t smem = std::max<size_t>(std::max<size_t>(static_cast<size_t>(per) * 4, static_cast<size_t>(b + 2) * 8), 2048 * 8) + 64;
     if (smem > ctx->smem_optin - 24 * 1024) return ALQ_ERR_STATE;
     static size_t attr_set = 0;
     if (smem > attr_set) {

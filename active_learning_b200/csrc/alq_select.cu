@@ -300,15 +300,32 @@ merge_sorted_lists_kernel(const unsigned long long* __restrict__ keys, int lists
     if (key == ~0ull) return;                               // padding
     const int mine = static_cast<int>(i / len);
     int64_t rank = i - static_cast<int64_t>(mine) * len;
-    for (int r = 0; r < lists; ++r) {
-        if (r == mine) continue;
-        const unsigned long long* base = keys + static_cast<int64_t>(r) * len;
-        int64_t lo = 0, hi = len;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (base[mid] < key) lo = mid + 1; else hi = mid;
+    if (rank >= keep) return;
+    // the searches in the other lists are independent: 8 of them advance in lock step, so a word costs
+    // ~log2(len) dependent load rounds instead of lists * log2(len)
+    constexpr int W = 8;
+    for (int r0 = 0; r0 < lists; r0 += W) {
+        int64_t lo[W], hi[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            lo[w] = 0;
+            hi[w] = (r0 + w < lists && r0 + w != mine) ? len : 0;
         }
-        rank += lo;
+#pragma unroll 1
+        for (int step = 0; step < 40; ++step) {
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                if (lo[w] < hi[w]) {
+                    const int64_t mid = (lo[w] + hi[w]) >> 1;
+                    if (keys[static_cast<int64_t>(r0 + w) * len + mid] < key) lo[w] = mid + 1; else hi[w] = mid;
+                    any = true;
+                }
+            }
+            if (!any) break;
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) rank += lo[w];
         if (rank >= keep) return;
     }
     out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);

@@ -464,9 +464,16 @@ def run_own(args):
             "selection_overlap_with_gpu": (float(len(np.intersect1d(cp, res.numpy())) / BUDGET) if world == 1 else None)}
     if not args.no_extras:
         extras = {}
+        comm_error = None
         if world > 1:
-            eng.comm_init()
+            try:
+                eng.comm_init()
+            except Exception as exc:   # e.g. CUDA IPC unavailable: report, keep the headline line
+                comm_error = repr(exc)
         for kind in ("coreset", "badge"):
+            if comm_error:
+                extras[kind] = {"error": comm_error}
+                continue
             try:
                 extras[kind] = run_greedy_workload(eng, kind, peak, steps=args.extra_steps, warmup=1, world=world, rank=rank)
             except Exception as exc:  # report, never hide

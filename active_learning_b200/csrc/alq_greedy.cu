@@ -198,7 +198,8 @@ __device__ __forceinline__ void push_payload(const StepArgs& A, int local, float
 template <bool FACTORED, bool SAMPLE>
 __device__ __forceinline__ void publish_step(const StepArgs& A, int t, bool* sh_last) {
     const CommArgs& cm = A.cm;
-    __threadfence_system();                 // this thread's (remote) stores are ordered before the ticket
+    if (SAMPLE) __threadfence_system();     // this thread's remote min-distance stores are ordered before the ticket
+    else __threadfence();                   // arg-max: only the last CTA writes to peers
     __syncthreads();
     if (threadIdx.x == 0) *sh_last = (atomicAdd(&A.ticket[t], 1u) == gridDim.x - 1);
     __syncthreads();

@@ -208,6 +208,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 
+// ---- thread-block cluster helpers -------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 // ---- block-wide bitonic sort of `n` (power of two, >= 64, n/2 <= blockDim.x threads used... see below) -------
 // 64-bit keys ascending, data in shared memory `sk` on entry and exit.  Thread t owns elements (2t, 2t+1):
 // every compare-exchange at distance j <= 32 happens in registers / warp shuffles (partner element i ^ j lives in

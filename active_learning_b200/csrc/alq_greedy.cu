@@ -582,14 +582,6 @@ struct SampleArgs {
 constexpr int kSampThreads = 1024;
 constexpr int kCL = 8;             // CTAs per cluster == per partition (portable cluster size)
 
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
 
 // NumPy pairwise_sum leaf (n <= 128) evaluated by an 8-lane group, bit-exact:
 //   r[j] = a[j]; r[j] += a[i+j] for i = 8,16,..; ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); then the

@@ -34,14 +34,6 @@ struct Scratch {
 };
 #define SELC_STAMP(i) do { if (S.dbg && threadIdx.x == 0 && rank == 0) S.dbg[i] = clock64(); } while (0)
 
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
 __device__ __forceinline__ uint32_t score_key(float s) { return alq_ord(s + 0.0f); }
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)

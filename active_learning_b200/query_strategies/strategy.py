@@ -141,7 +141,7 @@ class EngineMixin:
         # save_experiment pickles the whole Strategy every round (utils/resume_training.py:49) and
         # train() pickles it into mp.spawn workers (strategy.py:297): keep handles and caches out.
         state = dict(self.__dict__)
-        for k in ("_engine", "_shard_group", "_saved_embeddings"):
+        for k in ("_engine", "_shard_group", "_saved_embeddings", "_emb_cache"):
             state.pop(k, None)
         return state
 
@@ -153,9 +153,67 @@ class EngineMixin:
         return DataLoader(Subset(self.al_set, indices=idxs), shuffle=False,
                           **self.train_args["loader_te_args"], drop_last=False)
 
+    # ---- cross-round embedding cache ---------------------------------
+    def _cacheable(self, net):
+        """Under --freeze_feature the encoder never changes (resnet_simclr.py:36-37 detaches it) and the
+        al_set transforms are deterministic, so pool embeddings are round-invariant; only the linear head
+        moves.  Needs the reference's encoder/linear layout and is opt-out with cache_embeddings=False."""
+        return (bool(getattr(self, "freeze_feature", False)) and getattr(self, "cache_embeddings", True)
+                and hasattr(net, "encoder") and hasattr(net, "linear"))
+
+    @staticmethod
+    def _encoder_fingerprint(net):
+        with torch.no_grad():
+            ps = list(net.encoder.parameters())
+            return (len(ps), float(sum(p.double().sum() for p in ps[:4]))) if ps else (0, 0.0)
+
+    def _forward_pool_cached(self, idxs, net, want_features):
+        """Same outputs as `_forward_pool`, but the encoder runs only for pool rows it has not seen: the
+        embeddings live in a device slab [n_pool, D] (1.28 M x 2048 fp32 = 10.5 GB on a 180 GB part) and each
+        query recomputes logits = linear(emb) per loader batch, exactly the GEMM the reference's forward ends
+        with (resnet_simclr.py:38).  8 AL rounds cost one backbone pass over the pool instead of 8."""
+        dev = self._query_device()
+        net.to(dev)
+        idxs_t = torch.as_tensor(np.asarray(idxs, dtype=np.int64), device=dev)
+        fp = self._encoder_fingerprint(net)
+        cache = getattr(self, "_emb_cache", None)
+        if cache is not None and (cache["fp"] != fp or cache["emb"].device != dev):
+            cache = None
+        bs = int(self.train_args["loader_te_args"]["batch_size"])
+        with torch.no_grad():
+            if cache is None or len(idxs) == 0:
+                have = None
+            else:
+                have = cache["have"][idxs_t]
+            missing = np.asarray(idxs, dtype=np.int64) if have is None else np.asarray(idxs, dtype=np.int64)[(~have).cpu().numpy()]
+            if len(missing):
+                off = 0
+                for x, _y, _i in self._loader(missing.tolist()):
+                    em = net.encoder(x.to(dev, non_blocking=True))
+                    if cache is None:
+                        dpad = (em.shape[1] + 3) & ~3
+                        cache = {"fp": fp, "dim": em.shape[1],
+                                 "emb": torch.zeros((self.n_pool, dpad), dtype=torch.float32, device=dev),
+                                 "have": torch.zeros(self.n_pool, dtype=torch.bool, device=dev)}
+                    rows = torch.as_tensor(missing[off:off + em.shape[0]], device=dev)
+                    cache["emb"][rows, :em.shape[1]] = em.float()
+                    cache["have"][rows] = True
+                    off += em.shape[0]
+                self._emb_cache = cache
+            if cache is None:
+                return (torch.empty((0, self.num_classes), dtype=torch.float32, device=dev),
+                        torch.empty((0, 4), dtype=torch.float32, device=dev))
+            emb = cache["emb"].index_select(0, idxs_t)
+            logits = torch.empty((len(idxs), self.num_classes), dtype=torch.float32, device=dev)
+            for lo in range(0, len(idxs), bs):
+                logits[lo:lo + bs] = net.linear(emb[lo:lo + bs, :cache["dim"]])
+        return logits, (emb if want_features else None)
+
     def _forward_pool(self, idxs, net, want_features):
         """Loader loop of margin_sampler.py:29-37 / coreset_sampler.py:50-56 with the `.cpu()`
         removed: outputs land in preallocated device slabs [len(idxs), C] / [len(idxs), D]."""
+        if self._cacheable(net):
+            return self._forward_pool_cached(idxs, net, want_features)
         dev = self._query_device()
         n = len(idxs)
         net.to(dev)

@@ -147,3 +147,86 @@ def test_drop_in_binding_on_foreign_base(gold):
     assert set(cls) >= {"MarginSampler", "CoresetSampler", "BADGESampler"}
     assert ForeignStrategy in cls["MarginSampler"].__mro__
     assert cls["MarginSampler"].query is not ForeignStrategy.query
+
+
+class _EncoderNet(torch.nn.Module):
+    """resnet_simclr.py layout: encoder -> (detached) -> linear; the forward counts encoder calls."""
+
+    def __init__(self, n_pool, d, c):
+        super().__init__()
+        self.table = torch.nn.Embedding(n_pool, d)
+        self.encoder = torch.nn.Sequential(torch.nn.Linear(d, d), torch.nn.ReLU())
+        self.linear = torch.nn.Linear(d, c)
+        self.encoder_rows = 0
+
+    def forward(self, x, return_features=False, specify_input_layer=None):
+        self.encoder_rows += len(x)
+        h = self.encoder(self.table(x.long())).detach()
+        out = self.linear(h)
+        return (out, h) if return_features else out
+
+
+def test_embedding_cache_across_rounds_matches_uncached():
+    """--freeze_feature: the encoder runs once per pool row over all rounds; picks equal the uncached run
+    even after the linear head changes between rounds (section 8f rank 1)."""
+    from helpers import FakeExperiment, IndexDataset
+    from active_learning_b200.query_strategies.get_strategy import get_strategy
+    import tempfile
+    n, d, c = 400, 16, 10
+    results = {}
+    for cached in (False, True):
+        torch.manual_seed(0)
+        net = _EncoderNet(n, d, c)
+
+        class CountingEncoder(torch.nn.Module):
+            def __init__(self, inner):
+                super().__init__()
+                self.inner, self.rows = inner, 0
+
+            def forward(self, x):
+                self.rows += len(x)
+                return self.inner(x)
+
+        ds = IndexDataset(n, c)
+        orig_getitem = ds.__getitem__
+
+        class DS(IndexDataset):
+            def __getitem__(self, i):
+                return net.table.weight.detach()[i].clone(), 0, i
+        ds = DS(n, c)
+        net.encoder = CountingEncoder(net.encoder)
+
+        class Net2(torch.nn.Module):
+            def __init__(self, enc, lin):
+                super().__init__()
+                self.encoder, self.linear = enc, lin
+
+            def forward(self, x, return_features=False, specify_input_layer=None):
+                h = self.encoder(x).detach()
+                o = self.linear(h)
+                return (o, h) if return_features else o
+        net2 = Net2(net.encoder, net.linear)
+        picks = []
+        for name in ("MarginSampler", "CoresetSampler", "BADGESampler"):
+            args = dict(early_stop_patience=0, n_epoch=1, world_size=1, model="m", freeze_feature=True,
+                        ckpt_path=tempfile.mkdtemp(), exp_name="t", subset_labeled=None, subset_unlabeled=None,
+                        partitions=1, cache_embeddings=cached)
+            s = get_strategy(name)(ds, ds, net2, {"loader_te_args": {"batch_size": 32, "num_workers": 0}},
+                                   np.arange(5), FakeExperiment(), None, **args)
+            s.init_network_weights()
+            s.set_engine(OracleEngine())
+            s.update(np.arange(5, 45), 40)
+            net2.encoder.rows = 0
+            for rd in range(3):
+                np.random.seed(rd)
+                idx, cost = s.query(20.0)
+                s.update(idx, cost)
+                picks.append(idx)
+                with torch.no_grad():                       # "training" moves only the head
+                    net2.linear.weight.add_(0.01 * (rd + 1))
+            if cached:
+                assert net2.encoder.rows <= n, (name, net2.encoder.rows)   # each pool row encoded at most once
+            elif name != "CoresetSampler":    # (CoreSet keeps the reference's own per-strategy cache, coreset_sampler.py:120)
+                assert net2.encoder.rows > n
+        results[cached] = picks
+    assert results[True] == results[False]

@@ -231,6 +231,8 @@ class Engine:
         desc.budget_host = budget_h.ctypes.data
         keep = [part_off_h, budget_h, picks, x, a]
         if uniforms is not None:
+            if vpos is None or full_n is None:
+                raise AlqError("D^2 sampling (uniforms given) needs vpos and full_n")
             u = np.ascontiguousarray(uniforms, dtype=np.float64)
             if u.size != total:
                 raise AlqError(f"need {total} uniforms, got {u.size}")

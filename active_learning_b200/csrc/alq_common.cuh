@@ -42,6 +42,8 @@ struct alq_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     int64_t launches = 0;
+    unsigned int* tile_counters = nullptr;   // ring of per-launch tile counters (dynamic scheduling of K1/K2)
+    int tile_counter_next = 0;
     AlqComm comm;
     int k3_impl = 0;          // 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32
     int select_impl = 0;      // 0 auto, 1 multi-kernel radix select, 2 cluster-resident single launch

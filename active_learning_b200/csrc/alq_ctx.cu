@@ -42,6 +42,7 @@ extern "C" void alq_destroy(alq_ctx* ctx) {
     alq_comm_destroy(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->arena2) cudaFree(ctx->arena2);
+    if (ctx->tile_counters) cudaFree(ctx->tile_counters);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->side_stream2) cudaStreamDestroy(ctx->side_stream2);

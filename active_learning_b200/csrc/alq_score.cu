@@ -149,17 +149,21 @@ __device__ __forceinline__ void load_row_smem(const float4* p, int lane, int nve
 template <int NV, int MODE>
 __global__ void __launch_bounds__(1024, 1)
 rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg cfg, float* __restrict__ scores,
-                 int bs, int64_t grow0, int64_t n_total, float* __restrict__ a, int64_t lda) {
+                 int bs, int64_t grow0, int64_t n_total, float* __restrict__ a, int64_t lda,
+                 unsigned int* __restrict__ tile_counter) {
     extern __shared__ __align__(128) unsigned char smem_rows[];
     float* tiles = reinterpret_cast<float*>(smem_rows);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(cfg.stages) * cfg.tile_floats);
     uint64_t* empty = full + cfg.stages;
+    int* s_tile = reinterpret_cast<int*>(empty + cfg.stages);          // tile index carried by each stage (-1: done)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = cfg.rows_per_tile;
-    // contiguous share of the rows for this CTA, in whole tiles
-    const int64_t tiles_total = (n + R - 1) / R;
-    const int64_t t_lo = tiles_total * blockIdx.x / gridDim.x, t_hi = tiles_total * (blockIdx.x + 1) / gridDim.x;
-    const int ntiles = static_cast<int>(t_hi - t_lo);
+    // Tiles are claimed dynamically (runs of kClaim consecutive tiles per atomicAdd): a CTA that starts late --
+    // e.g. because another stream's small kernel still holds its SM -- simply claims fewer tiles, so this
+    // kernel can overlap with the top-B kernel of the previous query without a straggler tail.
+    constexpr int kClaim = 8;
+    const int tiles_total = static_cast<int>((n + R - 1) / R);
+    const int teams = cfg.consumers / cfg.split;
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], cfg.split); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -168,25 +172,42 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
     const int nvec = c >> 2;
     if (warp == 0) {
         if (lane == 0) {
-            for (int i = 0; i < ntiles; ++i) {
+            int claim_lo = 0, claim_hi = 0, sentinels = 0;
+            bool exhausted = false;
+            for (int i = 0;; ++i) {
                 const int s = i % cfg.stages;
                 const uint32_t round = static_cast<uint32_t>(i / cfg.stages);
                 if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);
-                const int64_t row0 = (t_lo + i) * R;
-                const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
-                const uint32_t bytes = static_cast<uint32_t>(rr) * static_cast<uint32_t>(c) * 4u;
-                mbar_expect_tx(&full[s], bytes);
-                bulk_g2s(tiles + static_cast<size_t>(s) * cfg.tile_floats, logits + row0 * c, bytes, &full[s]);
+                if (claim_lo == claim_hi && !exhausted) {
+                    const unsigned int got = atomicAdd(tile_counter, static_cast<unsigned int>(kClaim));
+                    if (got >= static_cast<unsigned int>(tiles_total)) exhausted = true;
+                    else { claim_lo = static_cast<int>(got); claim_hi = min(tiles_total, claim_lo + kClaim); }
+                }
+                if (claim_lo < claim_hi) {
+                    const int tile = claim_lo++;
+                    const int64_t row0 = static_cast<int64_t>(tile) * R;
+                    const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
+                    const uint32_t bytes = static_cast<uint32_t>(rr) * static_cast<uint32_t>(c) * 4u;
+                    s_tile[s] = tile;
+                    mbar_expect_tx(&full[s], bytes);
+                    bulk_g2s(tiles + static_cast<size_t>(s) * cfg.tile_floats, logits + row0 * c, bytes, &full[s]);
+                } else {
+                    s_tile[s] = -1;                       // one sentinel per consumer team, then stop
+                    mbar_arrive(&full[s]);
+                    if (++sentinels == teams) break;
+                }
             }
         }
     } else {
         const int cw = warp - 1;
-        const int team = cw / cfg.split, sub = cw % cfg.split, teams = cfg.consumers / cfg.split;
-        for (int i = team; i < ntiles; i += teams) {
+        const int team = cw / cfg.split, sub = cw % cfg.split;
+        for (int i = team;; i += teams) {
             const int s = i % cfg.stages;
-            const int64_t row0 = (t_lo + i) * R;
-            const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
             mbar_wait(&full[s], static_cast<uint32_t>(i / cfg.stages) & 1u);
+            const int tile_idx = s_tile[s];
+            if (tile_idx < 0) break;
+            const int64_t row0 = static_cast<int64_t>(tile_idx) * R;
+            const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
             const float* tile = tiles + static_cast<size_t>(s) * cfg.tile_floats;
             float my_score = 0.f;
             for (int r = sub; r < rr; r += cfg.split) {
@@ -449,24 +470,42 @@ bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem) {
     while (split > 1 && (stages * split > 31 || split > R)) --split;
     cfg.rows_per_tile = R; cfg.stages = stages; cfg.consumers = stages * split; cfg.split = split;
     cfg.tile_floats = static_cast<int>(tile / 4);
-    smem = stages * tile + 2 * stages * sizeof(uint64_t) + 128;
+    smem = stages * tile + 2 * stages * sizeof(uint64_t) + stages * sizeof(int) + 128;
     return true;
 }
 
+// a zeroed tile counter for one launch: slots of a ring that is cleared once and again whenever it wraps
+unsigned int* next_tile_counter(alq_ctx* ctx, cudaStream_t st) {
+    constexpr int kSlots = 16384;
+    if (!ctx->tile_counters) {
+        if (cudaMalloc(&ctx->tile_counters, kSlots * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(ctx->tile_counters, 0, kSlots * sizeof(unsigned int));
+        ctx->tile_counter_next = 0;
+    }
+    if (ctx->tile_counter_next == kSlots) {
+        cudaMemsetAsync(ctx->tile_counters, 0, kSlots * sizeof(unsigned int), st);   // stream-ordered after its last users
+        ctx->tile_counter_next = 0;
+    }
+    return ctx->tile_counters + ctx->tile_counter_next++;
+}
+
 template <int NV, int MODE>
-cudaError_t launch_rows_pipe(const alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
+cudaError_t launch_rows_pipe(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
                              int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda) {
     cudaError_t e = cudaFuncSetAttribute(rows_pipe_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     const int64_t tiles_total = (n + cfg.rows_per_tile - 1) / cfg.rows_per_tile;
     const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles_total));
-    rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, row0, n_total, a, lda);
+    unsigned int* counter = next_tile_counter(ctx, st);
+    if (!counter) return cudaErrorMemoryAllocation;
+    rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, row0, n_total, a, lda,
+                                                                          counter);
     return cudaGetLastError();
 }
 
 template <int MODE>
-cudaError_t launch_rows_pipe_nv(const alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
+cudaError_t launch_rows_pipe_nv(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
                                 int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda) {
     const int nv = (c / 4 + 31) / 32;
     if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);

@@ -21,6 +21,7 @@
 // Every CTA sweeps the column tiles in the same order, so a Y tile is fetched from HBM once and
 // served to the other 147 CTAs from L2.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "alq_common.cuh"
 
@@ -340,8 +341,17 @@ int alq_min_dist_tc(alq_ctx* ctx, const float* x, int64_t ldx, const float* xn, 
     const size_t xae = static_cast<size_t>(n) * cpad, yae = static_cast<size_t>(m) * cpad;
     const int grid = ctx->sm_count;
     const int m_blocks = static_cast<int>((n + BM - 1) / BM), n_tiles = static_cast<int>((m + BN - 1) / BN);
-    const int rounds = m_blocks / grid, rem = m_blocks - rounds * grid;
-    const int items_per_cta = rounds + (rem ? rem + 1 : 0) + 1;
+    // Work list.  A CTA re-reads its row block (hi + lo = 2 MB at d = 2048) for every column tile, so the row
+    // blocks that are live at the same time must fit L2 next to the streamed Y tiles: with one row block per CTA
+    // (148 x 2 MB) they do not, and ncu showed 258 GB of DRAM reads for 5 GB of operands.  Instead `split` CTAs
+    // share a row block and divide its column tiles, so only grid / split (~37) row blocks are live per round.
+    const size_t blk_bytes = static_cast<size_t>(BM) * (d + cpad) * 8;
+    size_t live_mb = 64;                                                                              // <= 64 MB of row blocks
+    if (const char* e = getenv("ALQ_K3_LIVE_MB")) live_mb = static_cast<size_t>(std::max(1, atoi(e)));   // tuning aid
+    int live = static_cast<int>(std::max<size_t>(1, (live_mb << 20) / std::max<size_t>(blk_bytes, 1)));
+    live = std::max(1, std::min(live, grid));
+    const int rounds = (m_blocks + live - 1) / live;
+    const int items_per_cta = rounds + 1;
     int rc = alq_scratch_reserve(ctx, scratch_need({xe * 4, xe * 4, ye * 4, ye * 4, xae * 4, xae * 4, yae * 4, yae * 4,
                                                     static_cast<size_t>(n) * 4, static_cast<size_t>(m) * 4,
                                                     static_cast<size_t>(grid) * items_per_cta * sizeof(WorkItem),
@@ -356,28 +366,19 @@ int alq_min_dist_tc(alq_ctx* ctx, const float* x, int64_t ldx, const float* xn, 
     WorkItem* d_items = cur.take<WorkItem>(static_cast<size_t>(grid) * items_per_cta);
     int* d_counts = cur.take<int>(grid);
 
-    // ---- work list: full rounds (CTA c owns row block r*grid + c, all column tiles), then the remaining
-    //      row blocks cut into equal runs of column tiles
+    // ---- work list (see above): round r covers row blocks [r*live, r*live + mbs); CTA c takes part c % split of
+    //      the column tiles of row block c / split
     std::vector<WorkItem> items(static_cast<size_t>(grid) * items_per_cta);
     std::vector<int> counts(grid, 0);
-    auto push = [&](int cta, int mb, int nb, int ne) {
-        if (ne <= nb) return;
-        items[static_cast<size_t>(cta) * items_per_cta + counts[cta]++] = WorkItem{mb, nb, ne, 0};
-    };
-    for (int r = 0; r < rounds; ++r)
-        for (int cta = 0; cta < grid; ++cta) push(cta, r * grid + cta, 0, n_tiles);
-    if (rem) {
-        const int64_t total = static_cast<int64_t>(rem) * n_tiles;
-        const int64_t quota = (total + grid - 1) / grid;
-        int64_t at = 0;
-        for (int cta = 0; cta < grid && at < total; ++cta) {
-            int64_t end = std::min(total, at + quota);
-            while (at < end) {
-                const int mb = static_cast<int>(at / n_tiles), nb = static_cast<int>(at % n_tiles);
-                const int ne = static_cast<int>(std::min<int64_t>(n_tiles, nb + (end - at)));
-                push(cta, rounds * grid + mb, nb, ne);
-                at += ne - nb;
-            }
+    for (int r = 0; r < rounds; ++r) {
+        const int mb0 = r * live, mbs = std::min(live, m_blocks - mb0);
+        const int split = std::max(1, grid / mbs);
+        for (int cta = 0; cta < grid; ++cta) {
+            const int which = cta / split, part = cta % split;
+            if (which >= mbs) continue;
+            const int nb = static_cast<int>(static_cast<int64_t>(n_tiles) * part / split);
+            const int ne = static_cast<int>(static_cast<int64_t>(n_tiles) * (part + 1) / split);
+            if (ne > nb) items[static_cast<size_t>(cta) * items_per_cta + counts[cta]++] = WorkItem{mb0 + which, nb, ne, 0};
         }
     }
     ALQ_CUDA(ctx, cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));

@@ -346,7 +346,7 @@ int alq_min_dist_tc(alq_ctx* ctx, const float* x, int64_t ldx, const float* xn, 
     // (148 x 2 MB) they do not, and ncu showed 258 GB of DRAM reads for 5 GB of operands.  Instead `split` CTAs
     // share a row block and divide its column tiles, so only grid / split (~37) row blocks are live per round.
     const size_t blk_bytes = static_cast<size_t>(BM) * (d + cpad) * 8;
-    size_t live_mb = 64;                                                                              // <= 64 MB of row blocks
+    size_t live_mb = 48;                                                                              // sweep: 32-48 MB best
     if (const char* e = getenv("ALQ_K3_LIVE_MB")) live_mb = static_cast<size_t>(std::max(1, atoi(e)));   // tuning aid
     int live = static_cast<int>(std::max<size_t>(1, (live_mb << 20) / std::max<size_t>(blk_bytes, 1)));
     live = std::max(1, std::min(live, grid));

@@ -220,6 +220,7 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
                     const RowStats st = row_stats_vec<NV, false, true, false>(v, lane, nvec);
                     const int64_t row = row0 + r;
                     const float inv_bs = batch_scale(grow0 + row, n_total, bs);
+                    const float inv_s = 1.0f / st.s;          // one division per row; p = e * (1/s) is within 1 ulp of e / s
                     float4* q = reinterpret_cast<float4*>(a + row * lda);
                     float nn = 0.f;
 #pragma unroll
@@ -229,7 +230,7 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
                             float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float pj = exp_neg(e[j] - st.m) / st.s;
+                                const float pj = exp_neg(e[j] - st.m) * inv_s;
                                 const float g = (pj - ((idx * 4 + j) == st.arg ? 1.0f : 0.0f)) * inv_bs;
                                 e[j] = g;
                                 nn += g * g;
@@ -297,6 +298,7 @@ badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int
         load_row_vec<NV>(p, lane, nvec, v);
         const RowStats r = row_stats_vec<NV, false, true, false>(v, lane, nvec);
         const float inv_bs = batch_scale(row0 + row, n_total, bs);
+        const float inv_s = 1.0f / r.s;
         float4* q = reinterpret_cast<float4*>(a + row * lda);
         float nn = 0.f;
 #pragma unroll
@@ -306,7 +308,7 @@ badge_factors_vec_kernel(const float* __restrict__ logits, int64_t n, int c, int
                 float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float pj = exp_neg(e[j] - r.m) / r.s;
+                    const float pj = exp_neg(e[j] - r.m) * inv_s;
                     const float g = (pj - ((idx * 4 + j) == r.arg ? 1.0f : 0.0f)) * inv_bs;
                     e[j] = g;
                     nn += g * g;

@@ -341,7 +341,13 @@ def run_own(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     group = None
+    # stdout carries exactly ONE JSON line: libraries that print banners there (NCCL prints its version on the
+    # first communicator) are pointed at stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from active_learning_b200.sharding import ShardGroup
         group = ShardGroup()
@@ -519,9 +525,12 @@ def run_own(args):
             torch.cuda.empty_cache()
         line["workloads"] = extras
         line["gpu_launches_total"] = int(eng.launches - launches0)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if group is not None:
+        os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
 

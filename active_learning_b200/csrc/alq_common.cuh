@@ -25,7 +25,30 @@ struct AlqComm {            // peer-memory group (alq_comm.cu)
     size_t bytes = 0;
     unsigned long long epoch = 0;     // bumped per collective call: flags are epoch-tagged, never reset
     bool connected = false;
+    // tail of the window reserved for the top-B exchange (alq_topb_exchange): 2 parities x world lists + flags
+    static constexpr size_t kTopbWords = 16384;
+    size_t topb_region_bytes() const { return 2 * (static_cast<size_t>(world) * kTopbWords * 8 + 1024); }
+    size_t greedy_bytes() const { return bytes > topb_region_bytes() ? bytes - topb_region_bytes() : 0; }
 };
+
+// system-scope flag helpers shared by the multi-GPU kernels
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// bounded spin: a dead peer must not hang the GPU (sets a sticky status instead)
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want, int* status) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) != want) {
+        if (clock64() - t0 > 8000000000LL) { if (status) atomicExch(status, ALQ_ERR_STATE); return false; }
+        __nanosleep(64);
+    }
+    return true;
+}
 
 struct alq_ctx {
     int device = 0;

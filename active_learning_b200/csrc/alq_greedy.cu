@@ -53,23 +53,6 @@ struct CommArgs {
     int payload_floats;
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// bounded spin: a dead peer must not hang the GPU (sets a sticky status instead)
-__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want, int* status) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(p) != want) {
-        if (clock64() - t0 > 8000000000LL) { atomicExch(status, ALQ_ERR_STATE); return false; }
-        __nanosleep(64);
-    }
-    return true;
-}
 __device__ __forceinline__ char* slot_ptr(const CommArgs& cm, int peer, int ring, int src) {
     return cm.peer[peer] + cm.slot_off + (static_cast<size_t>(ring) * cm.world + src) * cm.slot_bytes;
 }
@@ -1127,8 +1110,8 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         const size_t mf = up((static_cast<size_t>(sample ? D->full_n_host[0] : 0) + 4) * 4);
         cm.mfull_off[0] = off; off += mf;
         cm.mfull_off[1] = off; off += mf;
-        if (off > G.bytes)
-            ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_greedy_select: peer window too small (%zu needed, %zu allocated)", off, G.bytes);
+        if (off > G.greedy_bytes())
+            ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_greedy_select: peer window too small (%zu needed, %zu usable)", off, G.greedy_bytes());
         ctx->comm.epoch += 1;
         cm.tag = ctx->comm.epoch << 32;
     }

@@ -485,6 +485,113 @@ extern "C" int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int
     return ALQ_OK;
 }
 
+// ---- the same exchange without NCCL: every rank writes its packed winners straight into every peer's window
+//      (st.global on CUDA-IPC mappings over NVLink) and raises an epoch-tagged flag; the merge kernel spins on
+//      the G flags of its own window and merges the G sorted lists.  Two launches, no collective call.
+namespace {
+struct TopbXchg {
+    int world, rank;
+    char* peer[ALQ_MAX_WORLD];
+    size_t words_off, flags_off;      // this call's parity half of the reserved region
+    unsigned long long tag;
+    unsigned int* ticket;
+    int* status;
+};
+
+__global__ void __launch_bounds__(256)
+topb_push_kernel(const float* __restrict__ scores, const int32_t* __restrict__ pos, int64_t k, int64_t row_lo,
+                 int64_t b, TopbXchg X) {
+    __shared__ bool last;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < b) {
+        unsigned long long v = ~0ull;
+        if (i < k) {
+            const int32_t p = pos[i];
+            v = (static_cast<unsigned long long>(score_key(scores[p])) << 32) | static_cast<uint32_t>(row_lo + p);
+        }
+        for (int g = 0; g < X.world; ++g)
+            reinterpret_cast<unsigned long long*>(X.peer[g] + X.words_off)[static_cast<int64_t>(X.rank) * b + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(X.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x < X.world)
+        st_release_sys(reinterpret_cast<unsigned long long*>(X.peer[threadIdx.x] + X.flags_off) + X.rank, X.tag);
+}
+
+__global__ void __launch_bounds__(256)
+topb_wait_merge_kernel(TopbXchg X, int64_t len, int32_t* __restrict__ out_pos, int64_t keep) {
+    if (threadIdx.x == 0)
+        for (int r = 0; r < X.world; ++r)
+            wait_flag(reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.flags_off) + r, X.tag, X.status);
+    __syncthreads();
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.words_off);
+    const int lists = X.world;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= lists * len) return;
+    const unsigned long long key = __ldcg(keys + i);
+    if (key == ~0ull) return;
+    const int mine = static_cast<int>(i / len);
+    int64_t rank = i - static_cast<int64_t>(mine) * len;
+    if (rank >= keep) return;
+    int64_t lo[ALQ_MAX_WORLD], hi[ALQ_MAX_WORLD];
+#pragma unroll
+    for (int w = 0; w < ALQ_MAX_WORLD; ++w) { lo[w] = 0; hi[w] = (w < lists && w != mine) ? len : 0; }
+#pragma unroll 1
+    for (int step = 0; step < 40; ++step) {
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < ALQ_MAX_WORLD; ++w) {
+            if (lo[w] < hi[w]) {
+                const int64_t mid = (lo[w] + hi[w]) >> 1;
+                if (__ldcg(keys + static_cast<int64_t>(w) * len + mid) < key) lo[w] = mid + 1; else hi[w] = mid;
+                any = true;
+            }
+        }
+        if (!any) break;
+    }
+#pragma unroll
+    for (int w = 0; w < ALQ_MAX_WORLD; ++w) rank += lo[w];
+    if (rank < keep) out_pos[rank] = static_cast<int32_t>(key & 0xffffffffu);
+}
+}  // namespace
+
+extern "C" int alq_topb_exchange(alq_ctx* ctx, const float* scores, const int32_t* pos, int64_t k, int64_t row_lo,
+                                 int64_t b, int32_t* out_gpos, void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    AlqComm& G = ctx->comm;
+    if (G.world <= 1 || !G.connected) ALQ_FAIL(ctx, ALQ_ERR_STATE, "alq_topb_exchange: no multi-GPU group (alq_comm_create/connect)");
+    if (k < 0 || b < 1 || k > b || b > static_cast<int64_t>(AlqComm::kTopbWords) || !out_gpos || (k > 0 && (!scores || !pos)))
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_topb_exchange: bad arguments (k=%lld b=%lld, b <= %zu)", (long long)k, (long long)b,
+                 AlqComm::kTopbWords);
+    if (G.bytes < 2 * G.topb_region_bytes()) ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_topb_exchange: peer window too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = alq_scratch_reserve(ctx, scratch_need({8, 8}));
+    if (rc) return rc;
+    ScratchCursor cur(ctx->scratch);
+    unsigned int* ticket = cur.take<unsigned int>(1);
+    int* status = cur.take<int>(1);
+    ALQ_CUDA(ctx, cudaMemsetAsync(ticket, 0, 4, st));
+    ALQ_CUDA(ctx, cudaMemsetAsync(status, 0, 4, st));
+    G.epoch += 1;
+    TopbXchg X{};
+    X.world = G.world; X.rank = G.rank;
+    for (int r = 0; r < G.world; ++r) X.peer[r] = G.peer[r];
+    const size_t half = G.topb_region_bytes() / 2;
+    const size_t base = G.bytes - G.topb_region_bytes() + (G.epoch & 1) * half;
+    X.words_off = base;
+    X.flags_off = base + static_cast<size_t>(G.world) * AlqComm::kTopbWords * 8;
+    X.tag = G.epoch << 32;
+    X.ticket = ticket; X.status = status;
+    const int blocks = static_cast<int>((b + 255) / 256);
+    topb_push_kernel<<<blocks, 256, 0, st>>>(scores, pos, k, row_lo, b, X);
+    ALQ_LAUNCH_CHECK(ctx);
+    topb_wait_merge_kernel<<<static_cast<int>((G.world * b + 255) / 256), 256, 0, st>>>(X, b, out_gpos, b);
+    ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}
+
 // Host-buffer entry point: H2D of the logits in row chunks on two side streams, K1 on each chunk
 // as soon as it lands, then the select on the second stream and the B positions back.
 extern "C" int alq_uncertainty_query_host(alq_ctx* ctx, const float* logits_host, int64_t n, int32_t c,

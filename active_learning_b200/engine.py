@@ -82,6 +82,7 @@ class Engine:
         blob = b"".join(handles)
         self._check(self.lib.alq_comm_connect(self._h, blob), "alq_comm_connect")
         self.world, self.rank = world, rank
+        self.comm_ready = True
         return self
 
     def set_option(self, key: str, value: int):
@@ -125,6 +126,14 @@ class Engine:
         out = torch.empty(int(b), dtype=torch.int32, device=keys.device)
         self._check(self.lib.alq_topb_merge(self._h, _ptr(keys), keys.numel(), int(list_len), int(b), _ptr(out),
                                             self._stream()), "alq_topb_merge")
+        return out
+
+    def topb_exchange(self, scores: torch.Tensor, pos: torch.Tensor, row_lo: int, b: int) -> torch.Tensor:
+        """Global top-b over the ranks of the peer-memory group (comm_init): every rank contributes its local winners
+        and gets the b global positions (int32, device) -- no NCCL call."""
+        out = torch.empty(int(b), dtype=torch.int32, device=scores.device)
+        self._check(self.lib.alq_topb_exchange(self._h, _ptr(scores), _ptr(pos), pos.numel(), int(row_lo), int(b),
+                                               _ptr(out), self._stream()), "alq_topb_exchange")
         return out
 
     def uncertainty_query_host(self, logits_host: torch.Tensor, mode: int, b: int) -> np.ndarray:

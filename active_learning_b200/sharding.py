@@ -41,6 +41,10 @@ class ShardGroup:
         every rank runs the same device merge: ascending words == ascending (score, position), i.e.
         exactly the single-GPU K1b order.  Only the B winning positions go to the host."""
         b = int(budget)
+        if getattr(engine, "comm_ready", False) and b <= 16384:
+            # peer-memory windows (Engine.comm_init): packed winners are stored straight into every rank's window
+            out = engine.topb_exchange(scores_local, pos_local, row_lo, b)
+            return out if not to_host else out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
         key = (b, scores_local.device)
         if self._buf.get("key") != key:
             self._buf = {"key": key,

@@ -353,6 +353,12 @@ def run_own(args):
         group = ShardGroup()
     eng = Engine(local)
     dev = eng.device
+    comm_error = None
+    if world > 1:
+        try:
+            eng.comm_init()          # peer-memory windows: top-B exchange and the global selection loops use them
+        except Exception as exc:     # e.g. CUDA IPC unavailable: fall back to the NCCL all-gather for the top-B merge
+            comm_error = repr(exc)
     peak, peak_src = measured_peaks()
     MODE_MARGIN = 0
 
@@ -508,12 +514,6 @@ def run_own(args):
             "selection_overlap_with_gpu": (float(len(np.intersect1d(cp, res.numpy())) / BUDGET) if world == 1 else None)}
     if not args.no_extras:
         extras = {}
-        comm_error = None
-        if world > 1:
-            try:
-                eng.comm_init()
-            except Exception as exc:   # e.g. CUDA IPC unavailable: report, keep the headline line
-                comm_error = repr(exc)
         for kind in ("coreset", "badge"):
             if comm_error:
                 extras[kind] = {"error": comm_error}

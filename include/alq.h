@@ -87,6 +87,12 @@ int alq_topb_pack(alq_ctx* ctx, const float* scores, const int32_t* pos, int64_t
 int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int64_t list_len, int64_t b,
                    int32_t* out_gpos, void* stream);
 
+/* The same exchange over the peer-memory windows of alq_comm_create/connect instead of a collective library:
+ * pack + store into every peer's window + flag, then wait + merge (b <= 16384).  Collective: every rank of the
+ * group must call it, in the same order relative to its other group calls.                      */
+int alq_topb_exchange(alq_ctx* ctx, const float* scores, const int32_t* pos, int64_t k, int64_t row_lo,
+                      int64_t b, int32_t* out_gpos, void* stream);
+
 /* Same tail for HOST buffers (what a CPU-tensor caller of MarginSampler.query has): pinned or
  * pageable host logits -> chunked H2D overlapped with K1 -> K1b -> positions back on the host.
  * Synchronous.                                                                                */

@@ -137,10 +137,13 @@ class CoresetQuery(EngineMixin):
 
     # ---- coreset_sampler.py:107-133 / badge_sampler.py:50-78 ---------------------------------------
     def query(self, budget):
+        union = np.asarray(self.get_idxs_for_coreset(), dtype=np.int64)      # RNG: two permutations (:22-23)
         group = getattr(self, "_shard_group", None)
         if group is not None and group.world_size > 1:
-            return self._query_global_sharded(budget, group)
-        union = np.asarray(self.get_idxs_for_coreset(), dtype=np.int64)
+            is_lab = self.already_labeled_idxs(boolean=True)[union]
+            shares = [int((~is_lab[a:b]).sum()) for a, b in (group.row_range(len(union), q) for q in range(group.world_size))]
+            if min(shares) > 0:                  # every rank owns candidates: shard; else every rank runs the whole query
+                return self._query_global_sharded(union, budget, group)
         cacheable = (self.freeze_feature and not self.GRADIENT_EMBEDDING
                      and self.subset_unlabeled is None and self.subset_labeled is None)
         saved = getattr(self, "_saved_embeddings", None)
@@ -161,13 +164,12 @@ class CoresetQuery(EngineMixin):
         return labeled_idxs_cur_rd, len(labeled_idxs_cur_rd)
 
     # ---- the same query with the rows of the union sharded over the ranks of a ShardGroup -------------
-    def _query_global_sharded(self, budget, group):
+    def _query_global_sharded(self, union, budget, group):
         """Every rank forwards rows [lo, hi) of the sorted union, keeps its unlabeled rows as candidates,
         receives the (few) labeled rows of the other ranks, and the selection loop exchanges its per-step
         winner through the engine's peer-memory windows.  Host bookkeeping and the RNG stream are replicated,
         so every rank returns the same list as the single-GPU query."""
         eng = self.get_engine()
-        union = np.asarray(self.get_idxs_for_coreset(), dtype=np.int64)
         is_lab = self.already_labeled_idxs(boolean=True)[union]
         budget = int(min(self.available_query_idxs(boolean=True)[union].sum(), budget))
         if budget <= 0:

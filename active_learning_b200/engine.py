@@ -75,6 +75,10 @@ class Engine:
         exchange their per-step winner from inside the kernels, with no host or NCCL call per step."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        if getattr(self, "comm_ready", False):  # idempotent: samplers and benches may both ask for it
+            if (world, rank) != (self.world, self.rank):
+                raise AlqError("comm_init: engine is already connected to a different process group")
+            return self
         handle = (C.c_char * 64)()
         self._check(self.lib.alq_comm_create(self._h, world, rank, int(window_bytes), handle), "alq_comm_create")
         handles = [None] * world

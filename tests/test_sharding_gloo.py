@@ -40,6 +40,14 @@ def _worker(rank, world, port, path, out_path):
         np.random.seed(21)
         res[name] = [int(i) for i in s.query(50.0)[0]]
     assert group.row_range(11, 0) == (0, 6) and group.row_range(11, 1) == (6, 11)
+    # ragged row gather (labeled rows of the global CoreSet query): rank order, padding dropped, empty rank ok
+    counts = [3, 0] if world == 2 else [3] * world
+    mine = torch.full((counts[rank], 5), float(rank + 1))
+    allr = group.all_gather_rows(mine, counts)
+    assert allr.shape == (sum(counts), 5) and bool((allr[:3] == 1.0).all())
+    vec = group.all_gather_rows(torch.arange(2 + rank, dtype=torch.int64), [2 + q for q in range(world)])
+    assert vec.tolist() == [i for q in range(world) for i in range(2 + q)]
+    assert sorted(group.my_partitions(5, 0) + group.my_partitions(5, 1)) == list(range(5))
     if rank == 0:
         np.save(out_path, np.array([res], dtype=object), allow_pickle=True)
     dist.barrier()

@@ -11,7 +11,8 @@ own code (imported in the build container from /root/reference/src with a comet_
 ``tests/golden/make_golden.py``; the resulting vectors are committed under ``tests/golden/``
 and ``tests/test_oracle_golden.py`` replays them.  The one exception is ``entropy`` scoring:
 the reference has no EntropySampler (SURVEY.md finding 1), so that mode is *parity unpinned*
-and its spec is defined here.
+and its spec is defined here.  The MASE / BASE functions at the end
+are pinned the same way by ``tests/golden/make_golden_mase.py``.
 
 All citations are relative to /root/reference/src/query_strategies/.
 """
@@ -329,3 +330,83 @@ def partition_idxs(input_idxs, partitions: int):
         out.append(idxs[cum:cum + m])
         cum += m
     return out
+
+
+# --------------------------------------------------------------------------------------
+# MASE / BASE  (mase_sampler.py:29-102, base_sampler.py:12-44)
+# --------------------------------------------------------------------------------------
+def mase_margins(emb: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, batch_size: int = 128):
+    """Distance of every embedding to each pairwise decision boundary of the linear head, restated from
+    mase_sampler.py:52-80 batch by batch with the reference's own broadcast arithmetic:
+        pred = argmax(linear(h));  wd = w_pred - w_c;  lam = 2 (h.wd + b_pred - b_c) / |wd|^2;
+        radius_c = | -wd * lam / 2 |;  NaN (c == pred, duplicated class rows) -> inf;  min over c.
+    Returns (min_margins [N], per_class_margins [N, C], pred [N])."""
+    emb = emb.detach().to(torch.float32).cpu()
+    weight = weight.detach().to(torch.float32).cpu()
+    bias = bias.detach().to(torch.float32).cpu()
+    mins, radii, preds = [], [], []
+    for lo in range(0, emb.shape[0], batch_size):
+        h = emb[lo:lo + batch_size]
+        logits = F.linear(h, weight, bias)
+        pred = logits.max(dim=1).indices                                   # :57
+        wd = weight[pred, :][:, None, :] - weight[None, :]                 # :60-62  (B, C, M)
+        bd = bias[pred, None] - bias[None, :]                              # :65
+        lam_num = 2 * ((h[:, None, :] * wd).sum(dim=2) + bd)               # :68
+        lam_den = (wd ** 2).sum(dim=2)                                     # :71
+        lam = lam_num / lam_den
+        eps = -wd * lam[:, :, None] / 2                                    # :74
+        radius = torch.linalg.norm(eps, dim=2)                             # :76
+        radius = torch.where(torch.isnan(radius), torch.tensor(float("inf")), radius)   # :77
+        m, _ = radius.min(dim=1)                                           # :79
+        mins.append(m)
+        radii.append(radius)
+        preds.append(pred)
+    if not mins:
+        c = weight.shape[0]
+        return torch.empty(0), torch.empty(0, c), torch.empty(0, dtype=torch.int64)
+    return torch.cat(mins), torch.cat(radii), torch.cat(preds)
+
+
+def mase_margins_closed_form(logits: torch.Tensor, weight: torch.Tensor):
+    """The same quantity with the algebra carried out: h.wd + b_pred - b_c is the logit gap z_pred - z_c, and
+    | -wd * lam / 2 | = |z_pred - z_c| / |w_pred - w_c|.  Equal to `mase_margins` up to fp32 rounding of the two
+    evaluation orders (checked in tests/test_oracle_golden_mase.py); this is the form a streaming kernel
+    evaluates, and the one usable at sizes where the (B, C, M) broadcast of the reference does not fit."""
+    z = logits.detach().to(torch.float32).cpu()
+    w = weight.detach().to(torch.float32).cpu()
+    pred = z.max(dim=1).indices
+    den = ((w[:, None, :] - w[None, :, :]) ** 2).sum(dim=2)                # [C, C]
+    gap = (z.gather(1, pred[:, None]) - z).abs()
+    radius = gap / den.sqrt()[pred]
+    radius = torch.where(torch.isnan(radius), torch.tensor(float("inf")), radius)
+    radius[torch.arange(z.shape[0]), pred] = float("inf")
+    return radius.min(dim=1).values, radius, pred
+
+
+def mase_query(min_margins: torch.Tensor, idxs_for_query: np.ndarray, budget):
+    """mase_sampler.py:23-27 under the fixed tie-break (stable)."""
+    budget = int(min(len(idxs_for_query), budget))
+    pos = select_smallest(min_margins, budget)
+    return np.asarray(idxs_for_query)[pos].tolist(), budget
+
+
+def base_select(min_margins: torch.Tensor, per_class_margins: torch.Tensor, pred: torch.Tensor,
+                budget: int, num_classes: int):
+    """base_sampler.py:22-38: class by class, the `budget // C (+1)` rows closest to that class's boundary --
+    rows predicted as c compete with their overall minimum margin, the others with their distance to class c;
+    rows already taken are pushed to inf.  Sorts are stable (fixed tie-break).  Returns pool positions in
+    pick order; raises like the reference's assert (:40) if a row would be taken twice."""
+    mm = min_margins.detach().to(torch.float32).cpu()
+    pc = per_class_margins.detach().to(torch.float32).cpu()
+    pred = pred.detach().cpu()
+    picked = []
+    for c in range(num_classes):
+        count = int(budget / num_classes) + int(c < budget % num_classes)
+        if count == 0:
+            continue
+        key = torch.where(pred == c, mm, pc[:, c])
+        if picked:
+            key[picked] = float("inf")
+        picked += select_smallest(key, count).tolist()
+    assert len(picked) == len(set(picked))
+    return np.asarray(picked, dtype=np.int64)

@@ -4,7 +4,7 @@
 
 #include "alq_common.cuh"
 
-extern "C" int alq_version(void) { return 3; }
+extern "C" int alq_version(void) { return 4; }
 
 extern "C" int alq_create(alq_ctx** out, int device) {
     if (!out) return ALQ_ERR_INVALID;

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 
 #include "alq_common.cuh"
+#include "alq_mase_rows.cuh"
 
 namespace {
 
@@ -145,12 +146,14 @@ __device__ __forceinline__ void load_row_smem(const float4* p, int lane, int nve
     }
 }
 
-// MODE 0..2: scores; MODE 3: BADGE factors (writes a[row, :] and a_norm2[row])
+// MODE 0..2: scores; MODE 3: BADGE factors (writes a[row, :] and a_norm2[row]);
+// MODE 4: MASE minimum margin + predicted class (K6, table reads pruned); MODE 5: MASE with the per-class radii written
+constexpr int MODE_MASE_MIN = 4, MODE_MASE_FULL = 5;
 template <int NV, int MODE>
 __global__ void __launch_bounds__(1024, 1)
 rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg cfg, float* __restrict__ scores,
                  int bs, int64_t grow0, int64_t n_total, float* __restrict__ a, int64_t lda,
-                 unsigned int* __restrict__ tile_counter) {
+                 unsigned int* __restrict__ tile_counter, MaseArgs mase) {
     extern __shared__ __align__(128) unsigned char smem_rows[];
     float* tiles = reinterpret_cast<float*>(smem_rows);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(cfg.stages) * cfg.tile_floats);
@@ -201,6 +204,7 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
     } else {
         const int cw = warp - 1;
         const int team = cw / cfg.split, sub = cw % cfg.split;
+        const float mase_ratio = (MODE == MODE_MASE_MIN) ? __ldg(mase.gmin + c) : 0.f;
         for (int i = team;; i += teams) {
             const int s = i % cfg.stages;
             mbar_wait(&full[s], static_cast<uint32_t>(i / cfg.stages) & 1u);
@@ -210,7 +214,18 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
             const int rr = static_cast<int>(min(static_cast<int64_t>(R), n - row0));
             const float* tile = tiles + static_cast<size_t>(s) * cfg.tile_floats;
             float my_score = 0.f;
+            int my_pred = 0;
             for (int r = sub; r < rr; r += cfg.split) {
+                if (MODE >= MODE_MASE_MIN) {
+                    const MaseRowSmem srow{reinterpret_cast<const float4*>(tile + static_cast<size_t>(r) * c), nvec};
+                    float mn;
+                    int arg;
+                    if (MODE == MODE_MASE_MIN) mase_row_min_smem<NV>(srow.p, nvec, lane, mase.ginv, mase.ldg, mase.gmin, mase_ratio, mn, arg);
+                    else mase_row_full<NV, true>(srow, lane, nvec, mase.ginv, mase.ldg,
+                                                 reinterpret_cast<float4*>(mase.radius + (row0 + r) * mase.ldr), mn, arg);
+                    if (lane == r) { my_score = mn; my_pred = arg; }
+                    continue;
+                }
                 float4 v[NV];
                 load_row_smem<NV>(reinterpret_cast<const float4*>(tile + static_cast<size_t>(r) * c), lane, nvec, v);
                 if (MODE < 3) {
@@ -244,7 +259,10 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);       // this warp's smem reads of the stage are done
-            if (lane < rr && (lane % cfg.split) == sub) scores[row0 + lane] = my_score;
+            if (lane < rr && (lane % cfg.split) == sub) {
+                scores[row0 + lane] = my_score;
+                if (MODE >= MODE_MASE_MIN) mase.pred[row0 + lane] = my_pred;
+            }
         }
     }
 }
@@ -493,7 +511,8 @@ unsigned int* next_tile_counter(alq_ctx* ctx, cudaStream_t st) {
 
 template <int NV, int MODE>
 cudaError_t launch_rows_pipe(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
-                             int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda) {
+                             int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda,
+                             const MaseArgs& mase = MaseArgs{}) {
     cudaError_t e = cudaFuncSetAttribute(rows_pipe_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -502,19 +521,20 @@ cudaError_t launch_rows_pipe(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cf
     unsigned int* counter = next_tile_counter(ctx, st);
     if (!counter) return cudaErrorMemoryAllocation;
     rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, row0, n_total, a, lda,
-                                                                          counter);
+                                                                          counter, mase);
     return cudaGetLastError();
 }
 
 template <int MODE>
 cudaError_t launch_rows_pipe_nv(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
-                                int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda) {
+                                int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda,
+                                const MaseArgs& mase = MaseArgs{}) {
     const int nv = (c / 4 + 31) / 32;
-    if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
-    if (nv <= 2) return launch_rows_pipe<2, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
-    if (nv <= 4) return launch_rows_pipe<4, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
-    if (nv <= 8) return launch_rows_pipe<8, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
-    return launch_rows_pipe<16, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda);
+    if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
+    if (nv <= 2) return launch_rows_pipe<2, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
+    if (nv <= 4) return launch_rows_pipe<4, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
+    if (nv <= 8) return launch_rows_pipe<8, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
+    return launch_rows_pipe<16, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
 }
 
 template <int NV>
@@ -529,6 +549,17 @@ void launch_score_vec(int mode, int grid, cudaStream_t st, const float* logits, 
 }
 
 }  // namespace
+
+// K6 through the same pipeline (declared in alq_mase_rows.cuh, called from alq_mase.cu)
+bool alq_mase_rows_pipe(alq_ctx* ctx, cudaStream_t st, const float* logits, int64_t n, int c, const MaseArgs& m,
+                        float* min_margin, cudaError_t* err) {
+    RowPipeCfg cfg{};
+    size_t smem = 0;
+    if (c > 2048 || !plan_row_pipe(ctx, c, cfg, smem)) return false;
+    *err = m.radius ? launch_rows_pipe_nv<MODE_MASE_FULL>(ctx, st, cfg, smem, logits, n, c, min_margin, 1, 0, n, nullptr, 0, m)
+                    : launch_rows_pipe_nv<MODE_MASE_MIN>(ctx, st, cfg, smem, logits, n, c, min_margin, 1, 0, n, nullptr, 0, m);
+    return true;
+}
 
 extern "C" int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,
                                  int32_t mode, float* scores, void* stream) {

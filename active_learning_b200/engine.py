@@ -212,6 +212,47 @@ class Engine:
                     "alq_argmin")
         return int(out.item())
 
+    # -- K6: MASE / BASE ---------------------------------------------------------------------------------
+    def class_gap_inv(self, weight: torch.Tensor):
+        """Head geometry of the linear classifier: (ginv [c, c padded to x4], gmin [c + 1]) with
+        ginv[a, c] = 1 / |w_a - w_c| (inf on the diagonal), gmin[a] = min_c ginv[a, c] and gmin[c] = the spread bound
+        of include/alq.h."""
+        weight = _f32c(weight, "weight")
+        c, m = weight.shape
+        ldg = (c + 3) & ~3
+        ginv = torch.empty((c, ldg), dtype=torch.float32, device=weight.device)
+        gmin = torch.empty(c + 1, dtype=torch.float32, device=weight.device)
+        self._check(self.lib.alq_class_gap_inv(self._h, _ptr(weight), c, m, _ld(weight), _ptr(ginv), ldg, _ptr(gmin),
+                                               self._stream()), "alq_class_gap_inv")
+        return ginv, gmin
+
+    def mase_margins(self, logits: torch.Tensor, gap, want_per_class: bool = False):
+        """(min_margin [n], pred [n] int32, radius [n, c] or None): mase_sampler.py:52-80 from the logits slab.
+        `gap` is what class_gap_inv returned."""
+        logits = _f32c(logits, "logits")
+        n, c = logits.shape
+        ginv, gmin = gap
+        if ginv.shape[0] != c or ginv.shape[1] < c or gmin.numel() != c + 1:
+            raise AlqError("mase_margins: the gap table does not match the class count of logits")
+        minm = torch.empty(n, dtype=torch.float32, device=logits.device)
+        pred = torch.empty(n, dtype=torch.int32, device=logits.device)
+        radius = torch.empty((n, c), dtype=torch.float32, device=logits.device) if want_per_class else None
+        self._check(self.lib.alq_mase_margins(self._h, _ptr(logits), n, c, _ld(logits), _ptr(ginv), _ld(ginv),
+                                              _ptr(gmin), _ptr(minm), _ptr(pred), _ptr(radius), c, self._stream()),
+                    "alq_mase_margins")
+        return minm, pred, radius
+
+    def base_select(self, min_margin: torch.Tensor, radius: torch.Tensor, pred: torch.Tensor, budget: int):
+        """base_sampler.py:22-38 on the device: int32 pool positions in pick order."""
+        radius, min_margin = _f32c(radius, "radius"), _f32c(min_margin, "min_margin")
+        if pred.dtype != torch.int32 or not pred.is_cuda:
+            raise AlqError("base_select: pred must be a CUDA int32 tensor")
+        n, c = radius.shape
+        out = torch.empty(int(budget), dtype=torch.int32, device=radius.device)
+        self._check(self.lib.alq_base_select(self._h, _ptr(min_margin), _ptr(radius), _ld(radius), _ptr(pred.contiguous()),
+                                             n, c, int(budget), _ptr(out), self._stream()), "alq_base_select")
+        return out
+
     # -- K4 / K5 ---------------------------------------------------------------------------------------
     def greedy_select(self, x: torch.Tensor, xn: torch.Tensor, mind: torch.Tensor,
                       part_off: Sequence[int], budget: Sequence[int],

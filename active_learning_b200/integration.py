@@ -15,6 +15,7 @@ from __future__ import annotations
 
 from .query_strategies.coreset import (BADGEQuery, CoresetQuery, PartitionedBADGEQuery,
                                        PartitionedCoresetQuery)
+from .query_strategies.mase import BASEQuery, MASEQuery
 from .query_strategies.uncertainty import ConfidenceQuery, EntropyQuery, MarginQuery
 
 _MIXINS = {
@@ -25,6 +26,8 @@ _MIXINS = {
     "PartitionedCoresetSampler": PartitionedCoresetQuery,
     "BADGESampler": BADGEQuery,
     "PartitionedBADGESampler": PartitionedBADGEQuery,
+    "MASESampler": MASEQuery,
+    "BASESampler": BASEQuery,
 }
 
 

@@ -1,20 +1,21 @@
 """`--strategy` dispatch, same contract as /root/reference/src/query_strategies/get_strategy.py:
-`get_strategy(name)` returns the class called `name`.  The seven samplers on the accelerated path
-plus the default RandomSampler are implemented; the reference's remaining class names resolve to a
+`get_strategy(name)` returns the class called `name`.  The nine accelerated samplers (the seven of the
+north-star path plus MASE / BASE) and the default RandomSampler are implemented; the reference's remaining class names resolve to a
 stub that raises a clear error (out of scope for this path)."""
 from .badge_sampler import BADGESampler  # noqa: F401
+from .base_sampler import BASESampler  # noqa: F401
 from .confidence_sampler import ConfidenceSampler  # noqa: F401
 from .coreset_sampler import CoresetSampler  # noqa: F401
 from .entropy_sampler import EntropySampler  # noqa: F401
 from .margin_sampler import MarginSampler  # noqa: F401
+from .mase_sampler import MASESampler  # noqa: F401
 from .partitioned_badge_sampler import PartitionedBADGESampler  # noqa: F401
 from .partitioned_coreset_sampler import PartitionedCoresetSampler  # noqa: F401
 from .random_sampler import RandomSampler  # noqa: F401
 
 ACCELERATED = ("MarginSampler", "ConfidenceSampler", "EntropySampler", "CoresetSampler",
-               "PartitionedCoresetSampler", "BADGESampler", "PartitionedBADGESampler")
-NOT_ON_THIS_PATH = ("BalancedRandomSampler", "BalancingSampler", "BASESampler",
-                    "MarginClusteringSampler", "MASESampler", "VAALSampler")
+               "PartitionedCoresetSampler", "BADGESampler", "PartitionedBADGESampler", "MASESampler", "BASESampler")
+NOT_ON_THIS_PATH = ("BalancedRandomSampler", "BalancingSampler", "MarginClusteringSampler", "VAALSampler")
 
 
 def _out_of_scope(name):

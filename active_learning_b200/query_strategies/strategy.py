@@ -149,8 +149,8 @@ class EngineMixin:
         eng = self.get_engine()
         return getattr(eng, "device", self.device)
 
-    def _loader(self, idxs):
-        return DataLoader(Subset(self.al_set, indices=idxs), shuffle=False,
+    def _loader(self, idxs, dataset=None):
+        return DataLoader(Subset(self.al_set if dataset is None else dataset, indices=idxs), shuffle=False,
                           **self.train_args["loader_te_args"], drop_last=False)
 
     # ---- cross-round embedding cache ---------------------------------
@@ -209,10 +209,12 @@ class EngineMixin:
                 logits[lo:lo + bs] = net.linear(emb[lo:lo + bs, :cache["dim"]])
         return logits, (emb if want_features else None)
 
-    def _forward_pool(self, idxs, net, want_features):
+    def _forward_pool(self, idxs, net, want_features, dataset=None, labels_out=None):
         """Loader loop of margin_sampler.py:29-37 / coreset_sampler.py:50-56 with the `.cpu()`
-        removed: outputs land in preallocated device slabs [len(idxs), C] / [len(idxs), D]."""
-        if self._cacheable(net):
+        removed: outputs land in preallocated device slabs [len(idxs), C] / [len(idxs), D].
+        `dataset` overrides al_set (mase_sampler.py:30-33 can read the augmented train_set); `labels_out`, a list,
+        collects the loader's label batches (mase_sampler.py:84).  Either one bypasses the embedding cache."""
+        if dataset is None and labels_out is None and self._cacheable(net):
             return self._forward_pool_cached(idxs, net, want_features)
         dev = self._query_device()
         n = len(idxs)
@@ -220,7 +222,9 @@ class EngineMixin:
         logits = emb = None
         off = 0
         with torch.no_grad():
-            for x, _y, _i in self._loader(idxs):
+            for x, _y, _i in self._loader(idxs, dataset):
+                if labels_out is not None:
+                    labels_out.append(torch.as_tensor(_y).clone())
                 x = x.to(dev, non_blocking=True)
                 if want_features:
                     lg, em = net(x, return_features="finalembed")

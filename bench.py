@@ -330,6 +330,55 @@ def run_greedy_workload(eng, kind, peak, steps, warmup, world=1, rank=0):
     }
 
 
+def run_mase_workload(eng, peak, steps, warmup, rank=0):
+    """MASE / BASE tails at the configs[1] shape: 80 000 x 1000 logits, a
+    1000 x 2048 linear head, B = 10 000.  Per GPU (rows are independent; at N > 1 every rank times its own shard)."""
+    dev = eng.device
+    g = torch.Generator(device=dev).manual_seed(2000 + rank)
+    logits = torch.randn(N_ROWS, N_CLASSES, device=dev, generator=g) * 3
+    weight = torch.randn(N_CLASSES, EMB_DIM, device=dev, generator=g) * 0.05
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    acc = {}
+    uniq = True
+    for it in range(warmup + steps):
+        ev[0].record()
+        ginv = eng.class_gap_inv(weight)
+        ev[1].record()
+        mm, pred, _ = eng.mase_margins(logits, ginv, want_per_class=False)
+        ev[2].record()
+        pos = eng.select_smallest(mm, BUDGET)
+        ev[3].record()
+        mm2, pred2, radius = eng.mase_margins(logits, ginv, want_per_class=True)
+        ev[4].record()
+        bpos = eng.base_select(mm2, radius, pred2, BUDGET)
+        ev[5].record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            for k, (a, b) in {"gap_table_ms": (0, 1), "k6_min_ms": (1, 2), "mase_select_ms": (2, 3),
+                              "k6_per_class_ms": (3, 4), "base_class_loop_ms": (4, 5)}.items():
+                acc[k] = acc.get(k, 0.0) + ev[a].elapsed_time(ev[b]) / steps
+            uniq = uniq and len(set(bpos.tolist())) == BUDGET and len(set(pos.tolist())) == BUDGET
+        del radius
+    mase_ms = acc["gap_table_ms"] + acc["k6_min_ms"] + acc["mase_select_ms"]
+    base_ms = acc["gap_table_ms"] + acc["k6_per_class_ms"] + acc["base_class_loop_ms"]
+    b_min, b_pc = 4 * N_CLASSES + 8, 8 * N_CLASSES + 8
+    return {
+        "workload": "MASESampler / BASESampler tails (logit-gap / head-geometry margins + stable selection), per GPU",
+        "rows": N_ROWS, "classes": N_CLASSES, "head_dim": EMB_DIM, "budget": BUDGET, "picks_unique": uniq,
+        "mase": {"value": N_ROWS / (mase_ms * 1e-3), "unit": "samples/s", "ms_per_step": mase_ms},
+        "base": {"value": N_ROWS / (base_ms * 1e-3), "unit": "samples/s", "ms_per_step": base_ms,
+                 "classes_with_picks": min(N_CLASSES, BUDGET)},
+        "breakdown_ms": acc,
+        "roofline": {"kernel": "mase_rows_vec_kernel<8,min-only> (K6)", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                     "achieved": N_ROWS * b_min / (acc["k6_min_ms"] * 1e-3) / 1e9,
+                     "frac": N_ROWS * b_min / (acc["k6_min_ms"] * 1e-3) / 1e9 / peak, "bytes_per_row": b_min,
+                     "note": "the 4 MB gap table is read through L2 and not counted"},
+        "roofline_per_class": {"kernel": "mase_rows_vec_kernel<8,per-class> (K6, BASE)", "bound": "hbm", "unit": "GB/s",
+                               "peak": peak, "achieved": N_ROWS * b_pc / (acc["k6_per_class_ms"] * 1e-3) / 1e9,
+                               "frac": N_ROWS * b_pc / (acc["k6_per_class_ms"] * 1e-3) / 1e9 / peak, "bytes_per_row": b_pc},
+    }
+
+
 # ----------------------------------------------------------------------------------------------
 # own arm
 # ----------------------------------------------------------------------------------------------
@@ -523,6 +572,11 @@ def run_own(args):
             except Exception as exc:  # report, never hide
                 extras[kind] = {"error": repr(exc)}
             torch.cuda.empty_cache()
+        try:
+            extras["mase_base"] = run_mase_workload(eng, peak, steps=args.extra_steps, warmup=1, rank=rank)
+        except Exception as exc:  # report, never hide
+            extras["mase_base"] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
         line["workloads"] = extras
         line["gpu_launches_total"] = int(eng.launches - launches0)
     sys.stdout.flush()

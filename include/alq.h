@@ -188,6 +188,35 @@ typedef struct alq_greedy_desc {
 
 int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* desc, void* stream);
 
+/* ---- K6: MASE / BASE ---------------------------------------------
+ * mase_sampler.py:52-80 measures, for every pool row, the distance of its embedding h_i to the decision
+ * boundary between the predicted class p = argmax z_i (lowest index on ties) and every other class c:
+ *     radius[i, c] = | -(w_p - w_c) * lam / 2 |,  lam = 2 (h_i.(w_p - w_c) + b_p - b_c) / |w_p - w_c|^2
+ *                  = |z_ip - z_ic| / |w_p - w_c|            (the logit gap over the head geometry),
+ * NaN (c == p, coinciding class rows) -> +inf (:77), min_margin[i] = min_c radius[i, c] (:79).
+ *
+ * alq_class_gap_inv: ginv[a, c] = 1 / |w_a - w_c| for the head weight[c, m] (:60-71; +inf where rows coincide and on
+ *   the diagonal; columns c..ldg-1 are filled with +inf) and, if gmin != NULL (c + 1 floats), gmin[a] = min_c ginv[a, c]
+ *   for a < c plus gmin[c] = max_a (largest finite ginv[a, :]) / gmin[a], the spread of the class rows.
+ *   Once per query: the head changes every round.
+ * alq_mase_margins: one streaming pass over the logits slab.  pred[i] = p;  radius may be NULL (MASE needs only
+ *   the minimum); columns c..ldr-1 of radius are unspecified.  gmin (optional, from alq_class_gap_inv of the same
+ *   table) lets the minimum-only pass skip every class that provably cannot attain it (the skip is verified per
+ *   row, with a full evaluation if the check fails) -- same result, the table is touched for a handful of
+ *   classes per row instead of all C.                                                                       */
+int alq_class_gap_inv(alq_ctx* ctx, const float* weight, int32_t c, int32_t m, int64_t ldw, float* ginv,
+                      int64_t ldg, float* gmin, void* stream);
+int alq_mase_margins(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, const float* ginv,
+                     int64_t ldg, const float* gmin, float* min_margin, int32_t* pred, float* radius, int64_t ldr,
+                     void* stream);
+
+/* base_sampler.py:22-38: class by class (c = 0..C-1), take the budget / C (+1 for c < budget % C) rows with the
+ * smallest key  (pred[i] == c ? min_margin[i] : radius[i, c]),  rows taken by earlier classes pushed to +inf;
+ * every per-class sort is K1b (stable).  out_pos[0..budget) = pool positions in pick order.  Synchronous.
+ * ALQ_ERR_NUMERIC if a row would be selected twice -- the condition the reference asserts on (:40).          */
+int alq_base_select(alq_ctx* ctx, const float* min_margin, const float* radius, int64_t ldr, const int32_t* pred,
+                    int64_t n, int32_t c, int64_t budget, int32_t* out_pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,27 @@ class LookupNet(nn.Module):
         return self.logits[i]
 
 
+class HeadNet(nn.Module):
+    """Embedding table + the linear head of the reference's models (resnet_simclr.py:21,29-41):
+    logits = linear(emb[x]); `specify_input_layer="finalembed"` applies the head alone."""
+
+    def __init__(self, emb, weight, bias):
+        super().__init__()
+        self.register_buffer("emb", emb.clone())
+        self.linear = nn.Linear(weight.shape[1], weight.shape[0])
+        with torch.no_grad():
+            self.linear.weight.copy_(weight)
+            self.linear.bias.copy_(bias)
+
+    def forward(self, x, return_features=False, specify_input_layer=None):
+        if specify_input_layer:
+            assert specify_input_layer == "finalembed"
+            return self.linear(x)
+        h = self.emb[x.long()]
+        out = self.linear(h)
+        return (out, h) if return_features else out
+
+
 class FakeExperiment:
     url = "."
 
@@ -50,11 +71,14 @@ class FakeExperiment:
         return lambda *a, **k: None
 
 
-def make_strategy(name, logits, emb, eval_idxs, labeled, batch_size, engine=None, **kw):
+def make_strategy(name, logits, emb, eval_idxs, labeled, batch_size, engine=None, net=None, **kw):
     from active_learning_b200.query_strategies.get_strategy import get_strategy
-    n, c = logits.shape
+    if net is None:
+        n, c = logits.shape
+        net = LookupNet(logits, emb)
+    else:                                   # a HeadNet: logits come out of its own linear head
+        n, c = net.emb.shape[0], net.linear.out_features
     ds = IndexDataset(n, c)
-    net = LookupNet(logits, emb)
     args = dict(early_stop_patience=0, n_epoch=1, world_size=1, model="SSLResNet18",
                 freeze_feature=True, ckpt_path=tempfile.mkdtemp(prefix="alq_test_"), exp_name="t",
                 subset_labeled=None, subset_unlabeled=None, partitions=1)
@@ -129,6 +153,24 @@ class OracleEngine:
 
     def argmin(self, v):
         return int(v.min(dim=0).indices.item())
+
+    def class_gap_inv(self, weight):
+        w = weight.detach().float()
+        den = ((w[:, None, :] - w[None, :, :]) ** 2).sum(dim=2)
+        g = 1.0 / den.sqrt()
+        g.fill_diagonal_(float("inf"))
+        return g, torch.cat([g.min(dim=1).values, torch.ones(1)])
+
+    def mase_margins(self, logits, gap, want_per_class=False):
+        ginv = gap[0]
+        pred = logits.max(dim=1).indices
+        r = (logits.gather(1, pred[:, None]) - logits).abs() * ginv[pred][:, :logits.shape[1]]
+        r = torch.where(torch.isnan(r), torch.tensor(float("inf")), r)
+        r[torch.arange(len(r)), pred] = float("inf")
+        return r.min(dim=1).values, pred.to(torch.int32), (r if want_per_class else None)
+
+    def base_select(self, min_margin, radius, pred, budget):
+        return torch.from_numpy(O.base_select(min_margin, radius, pred.long(), int(budget), radius.shape[1]).astype(np.int32))
 
     def greedy_select(self, x, xn, mind, part_off, budget, a=None, an=None, uniforms=None, vpos=None,
                       full_n=None, first_pick=None, variant=0, time_steps=False):

@@ -230,3 +230,56 @@ def test_embedding_cache_across_rounds_matches_uncached():
                 assert net2.encoder.rows > n
         results[cached] = picks
     assert results[True] == results[False]
+
+
+# ---- MASE / BASE -------------------------------------------------------
+@pytest.fixture(scope="module")
+def mgold():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return dict(np.load(os.path.join(root, "tests", "golden", "reference_golden_mase.npz")))
+
+
+def _mase_strategy(name, g, tag, engine):
+    from helpers import HeadNet
+    net = HeadNet(torch.from_numpy(g[f"{tag}_emb"]), torch.from_numpy(g[f"{tag}_weight"]),
+                  torch.from_numpy(g[f"{tag}_bias"]))
+    return make_strategy(name, None, None, g[f"{tag}_eval"], g[f"{tag}_labeled"], int(g[f"{tag}_bs"]),
+                         engine=engine, net=net)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mase_base_plumbing(mgold, tag):
+    g = mgold
+    budget = float(g[f"{tag}_budget"])
+    for name, key in (("MASESampler", "mase_picks"), ("BASESampler", "base_picks")):
+        s = _mase_strategy(name, g, tag, OracleEngine())
+        st0 = np.random.get_state()[1].copy()
+        idx, cost = s.query(budget)
+        assert idx == g[f"{tag}_{key}"].tolist() and cost == int(budget)
+        assert all(isinstance(i, int) for i in idx)
+        assert (np.random.get_state()[1] == st0).all()      # shuffle=False: no RNG draw (mase_sampler.py:20)
+        s.update(idx, cost)                                 # strategy.py:470 assertion holds
+        pickle.dumps(s)
+    # compute_margins keeps the reference's 4-tuple API (mase_sampler.py:29,102)
+    s = _mase_strategy("MASESampler", g, tag, OracleEngine())
+    pool = s.available_query_idxs(boolean=False, shuffle=False)
+    mm, pc, pred, true = s.compute_margins(pool)
+    assert mm.shape == (len(pool),) and pc.shape == (len(pool), s.num_classes)
+    assert pred.dtype == torch.int64 and len(true) == len(pool)
+    torch.testing.assert_close(mm, torch.from_numpy(g[f"{tag}_min_margins"]), rtol=1e-4, atol=2e-6)
+
+
+def test_mase_self_check_catches_a_wrong_head(mgold):
+    """mase_sampler.py:88-93: if the logits do not come from `linear(finalembed)`, the assertion trips."""
+    g = mgold
+    s = _mase_strategy("MASESampler", g, "a", OracleEngine())
+    real = s.net.forward
+
+    def skewed(x, return_features=False, specify_input_layer=None):
+        if specify_input_layer:
+            return real(x, specify_input_layer=specify_input_layer) * 1.5 + 0.3 * torch.arange(10.0)
+        return real(x, return_features=return_features)
+    s.net.forward = skewed
+    with pytest.raises(AssertionError):
+        s.query(10.0)

@@ -39,6 +39,14 @@ def _worker(rank, world, port, path, out_path):
         s._shard_group = group
         np.random.seed(21)
         res[name] = [int(i) for i in s.query(50.0)[0]]
+    # MASE rows sharded + merged; BASE margins sharded, class loop replicated on the gathered margins
+    from helpers import HeadNet
+    mg = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_mase.npz")))
+    for name in ("MASESampler", "BASESampler"):
+        net = HeadNet(torch.from_numpy(mg["a_emb"]), torch.from_numpy(mg["a_weight"]), torch.from_numpy(mg["a_bias"]))
+        s = make_strategy(name, None, None, mg["a_eval"], mg["a_labeled"], int(mg["a_bs"]), engine=OracleEngine(), net=net)
+        s._shard_group = group
+        res[name] = s.query(float(mg["a_budget"]))[0]
     assert group.row_range(11, 0) == (0, 6) and group.row_range(11, 1) == (6, 11)
     # ragged row gather (labeled rows of the global CoreSet query): rank order, padding dropped, empty rank ok
     counts = [3, 0] if world == 2 else [3] * world
@@ -66,6 +74,9 @@ def test_world_size_two_equals_single_process(gold):
     assert res["margin_f32_c10"] == gold["margin_f32_c10_picks"].tolist()
     assert res["PartitionedCoresetSampler"] == gold["e2e_PartitionedCoresetSampler_sub_int"].tolist()
     assert res["PartitionedBADGESampler"] == gold["e2e_PartitionedBADGESampler_sub_int"].tolist()
+    mg = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_mase.npz")))
+    assert res["MASESampler"] == mg["a_mase_picks"].tolist()
+    assert res["BASESampler"] == mg["a_base_picks"].tolist()
     # tie-heavy pool: the sharded result equals the single-process stable selection
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import OracleEngine, make_strategy

@@ -61,6 +61,7 @@ extern "C" int alq_set_option(alq_ctx* ctx, const char* key, int64_t value) {
     if (k == "k3_impl" && value >= 0 && value <= 2) ctx->k3_impl = static_cast<int>(value);
     else if (k == "greedy_variant" && value >= 0 && value <= 2) ctx->greedy_variant = static_cast<int>(value);
     else if (k == "select_impl" && value >= 0 && value <= 2) ctx->select_impl = static_cast<int>(value);
+    else if (k == "base_impl" && value >= 0 && value <= 2) ctx->base_impl = static_cast<int>(value);
     else ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_set_option: unknown option or value: %s=%lld", key, (long long)value);
     return ALQ_OK;
 }

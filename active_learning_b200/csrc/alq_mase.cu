@@ -9,6 +9,10 @@
 // [N, C] input K1 reads.  NaN (c == p, duplicated class rows: 0/0, x/0 * 0) becomes +inf like :77.
 // base_sampler.py:22-38 then selects class by class; alq_base_select runs that loop on the stream with K1b.
 #include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "alq_common.cuh"
 #include "alq_mase_rows.cuh"
@@ -255,6 +259,153 @@ __global__ void base_mark_kernel(const int32_t* __restrict__ picks, int cnt, uns
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// BASE with many classes and few picks per class (ImageNet: 1000 classes x 10): the class loop above is 1000 dependent
+// selections of ~30 us.  The dependence is only through the set of rows already taken, so it is split in two:
+//
+//   base_candidates_kernel  every class at once: the kBaseList smallest (key, row) pairs of each class, ignoring what
+//                           other classes take.  One CTA owns 8 adjacent classes (the 32-byte sector of a radius row),
+//                           streams the pool once, and every thread keeps the 3 smallest pairs it has seen per class in
+//                           shared memory plus, in a register, the smallest pair it dropped; the class's true top list
+//                           is inside the union of the kept pairs unless a dropped pair sorts before the list's last
+//                           entry -- checked exactly and reported in fail[class] (about 1e-4 per class).
+//   base_resolve_kernel     one warp walks the classes in order against a shared-memory bitset of taken rows: the first
+//                           cnt free rows of a class's list are what the sequential loop would have selected, provided
+//                           the list holds that many free rows with a finite key.  Otherwise it stops at that class; the
+//                           host runs the ordinary step for it and resumes after it.
+// The result is identical to the sequential loop (tests compare both with the oracle).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBaseGroup = 8;          // classes per CTA
+constexpr int kBaseThreads = 1024;
+constexpr int kBaseKeep = 3;           // pairs kept per thread and class
+constexpr int kBaseList = 64;          // candidate list length per class
+constexpr int kBaseMaxCnt = 32;        // picks per class the parallel path accepts (list = cnt + 32 spare)
+constexpr unsigned long long kBaseEmpty = ~0ull;
+
+__device__ __forceinline__ unsigned long long base_pack(float key, uint32_t row) {
+    return (static_cast<unsigned long long>(alq_ord(key + 0.0f)) << 32) | row;
+}
+
+__global__ void __launch_bounds__(kBaseThreads, 1)
+base_candidates_kernel(const float* __restrict__ minm, const float* __restrict__ radius, int64_t ldr,
+                       const int32_t* __restrict__ pred, int n, int c, int64_t budget,
+                       unsigned long long* __restrict__ cand_out, int* __restrict__ fail_out) {
+    extern __shared__ __align__(16) unsigned char smem_base[];
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_base);          // [group][keep][threads]
+    unsigned long long* tmp = cand + kBaseGroup * kBaseKeep * kBaseThreads;                // [2 * kBaseList]
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * kBaseGroup;
+    for (int i = tid; i < kBaseGroup * kBaseKeep * kBaseThreads; i += kBaseThreads) cand[i] = kBaseEmpty;
+    __syncthreads();
+    unsigned long long fourth[kBaseGroup];       // smallest pair this thread did NOT keep, per class
+#pragma unroll
+    for (int j = 0; j < kBaseGroup; ++j) fourth[j] = kBaseEmpty;
+    for (int i = tid; i < n; i += kBaseThreads) {
+        const int p = pred[i];
+        const float mm = minm[i];
+        const float* rrow = radius + static_cast<int64_t>(i) * ldr + c0;
+#pragma unroll
+        for (int j = 0; j < kBaseGroup; ++j) {
+            if (c0 + j < c) {
+                const float key = (p == c0 + j) ? mm : rrow[j];
+                const unsigned long long w = base_pack(key, static_cast<uint32_t>(i));
+                if (w < fourth[j]) {                            // rare after the first few rows
+                    unsigned long long* slot = cand + static_cast<size_t>(j) * kBaseKeep * kBaseThreads + tid;
+                    const unsigned long long k0 = slot[0], k1 = slot[kBaseThreads], k2 = slot[2 * kBaseThreads];
+                    if (w < k2) {                               // joins the kept three; the largest of them is dropped
+                        fourth[j] = k2;
+                        if (w < k0) { slot[0] = w; slot[kBaseThreads] = k0; slot[2 * kBaseThreads] = k1; }
+                        else if (w < k1) { slot[kBaseThreads] = w; slot[2 * kBaseThreads] = k1; }
+                        else slot[2 * kBaseThreads] = w;
+                    } else {
+                        fourth[j] = w;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < kBaseGroup; ++j) {
+        const int cls = c0 + j;
+        if (cls >= c) break;
+        const int64_t cnt = budget / c + (cls < budget % c ? 1 : 0);
+        if (cnt == 0) continue;                                 // uniform per CTA
+        unsigned long long* mine = cand + static_cast<size_t>(j) * kBaseKeep * kBaseThreads;
+        unsigned long long my_dropped = fourth[0];              // fourth[j] without dynamic indexing (keeps it in registers)
+#pragma unroll
+        for (int q = 1; q < kBaseGroup; ++q)
+            if (j == q) my_dropped = fourth[q];
+        const int len = static_cast<int>(cnt < kBaseList - 32 ? cnt + 32 : kBaseList);
+        alq_bitonic_sort_smem(mine, 2 * kBaseThreads);          // slots 0 and 1 of every thread
+        alq_bitonic_sort_smem(mine + 2 * kBaseThreads, kBaseThreads);   // slot 2
+        if (tid < kBaseList) { tmp[tid] = mine[tid]; tmp[kBaseList + tid] = mine[2 * kBaseThreads + tid]; }
+        __syncthreads();
+        alq_bitonic_sort_smem(tmp, 2 * kBaseList);
+        const unsigned long long last = tmp[len - 1];
+        // the list is the exact top-`len` unless some thread dropped a pair that sorts before the list's last entry
+        const int bad = __syncthreads_or(my_dropped < last);
+        if (tid < kBaseList) cand_out[static_cast<size_t>(cls) * kBaseList + tid] = tid < len ? tmp[tid] : kBaseEmpty;
+        if (tid == 0) fail_out[cls] = bad;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kBaseThreads, 1)
+base_resolve_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ fail, unsigned char* __restrict__ taken,
+                    int n, int c, int64_t budget, int c_begin, int32_t* __restrict__ out_pos, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_base[];
+    uint32_t* bits = reinterpret_cast<uint32_t*>(smem_base);
+    const int words = (n + 31) / 32;
+    for (int w = threadIdx.x; w < words; w += kBaseThreads) {
+        uint32_t v = 0;
+        const int lo = w * 32, hi = min(n, lo + 32);
+        for (int i = lo; i < hi; ++i) v |= (taken[i] ? 1u : 0u) << (i - lo);
+        bits[w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int64_t per = budget / c, extra = budget % c;
+    const uint32_t ord_inf = 0xff800000u;                        // alq_ord(+inf)
+    int cls = c_begin;
+    while (cls < c && per + (cls < extra ? 1 : 0) == 0) ++cls;
+    unsigned long long e0 = kBaseEmpty, e1 = kBaseEmpty;
+    int bad = 0;
+    if (cls < c) {
+        e0 = cand[static_cast<size_t>(cls) * kBaseList + lane];
+        e1 = cand[static_cast<size_t>(cls) * kBaseList + 32 + lane];
+        bad = fail[cls];
+    }
+    int result = c;
+    while (cls < c) {
+        int nxt = cls + 1;
+        while (nxt < c && per + (nxt < extra ? 1 : 0) == 0) ++nxt;
+        unsigned long long n0 = kBaseEmpty, n1 = kBaseEmpty;     // next class's list is in flight while this one resolves
+        int nbad = 0;
+        if (nxt < c) {
+            n0 = cand[static_cast<size_t>(nxt) * kBaseList + lane];
+            n1 = cand[static_cast<size_t>(nxt) * kBaseList + 32 + lane];
+            nbad = fail[nxt];
+        }
+        const int cnt = static_cast<int>(per + (cls < extra ? 1 : 0));
+        const int64_t off = static_cast<int64_t>(cls) * per + min(static_cast<int64_t>(cls), extra);
+        const int len = min(cnt + 32, kBaseList);
+        const uint32_t r0 = static_cast<uint32_t>(e0), r1 = static_cast<uint32_t>(e1);
+        const bool v0 = lane < len && static_cast<uint32_t>(e0 >> 32) < ord_inf && !((bits[r0 >> 5] >> (r0 & 31)) & 1u);
+        const bool v1 = lane + 32 < len && static_cast<uint32_t>(e1 >> 32) < ord_inf && !((bits[r1 >> 5] >> (r1 & 31)) & 1u);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, v0), b1 = __ballot_sync(0xffffffffu, v1);
+        if (bad || __popc(b0) + __popc(b1) < cnt) { result = cls; break; }
+        const uint32_t lt = (1u << lane) - 1u;
+        const int k0 = __popc(b0 & lt), k1 = __popc(b0) + __popc(b1 & lt);
+        if (v0 && k0 < cnt) { out_pos[off + k0] = static_cast<int32_t>(r0); atomicOr(&bits[r0 >> 5], 1u << (r0 & 31)); taken[r0] = 1; }
+        if (v1 && k1 < cnt) { out_pos[off + k1] = static_cast<int32_t>(r1); atomicOr(&bits[r1 >> 5], 1u << (r1 & 31)); taken[r1] = 1; }
+        __syncwarp();
+        cls = nxt; e0 = n0; e1 = n1; bad = nbad;
+    }
+    if (lane == 0) *status = result;
+}
+
 int rows_grid(const alq_ctx* ctx, int64_t n, int warps_per_block) {
     int64_t need = (n + warps_per_block - 1) / warps_per_block;
     const int64_t cap = static_cast<int64_t>(ctx->sm_count) * 8;
@@ -349,28 +500,66 @@ extern "C" int alq_base_select(alq_ctx* ctx, const float* min_margin, const floa
     if (budget == 0) return ALQ_OK;
     if (!min_margin || !radius || !pred || !out_pos) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_base_select: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t cnt_max = budget / c + (budget % c ? 1 : 0);
+    const size_t bitset_bytes = (static_cast<size_t>(n) + 31) / 32 * 4;
+    const size_t cand_smem = (static_cast<size_t>(kBaseGroup) * kBaseKeep * kBaseThreads + 2 * kBaseList) * sizeof(unsigned long long);
+    // many classes, few picks each: candidate lists for every class at once + an in-order resolve (base_impl: 1 = never)
+    const bool parallel = ctx->base_impl != 1 && cnt_max <= kBaseMaxCnt && (c >= 16 || ctx->base_impl == 2) &&
+                          bitset_bytes + 1024 <= ctx->smem_optin && cand_smem + 1024 <= ctx->smem_optin;
     // private arena: alq_select_smallest re-carves the shared scratch on every call
-    int rc = alq_arena2_reserve(ctx, scratch_need({static_cast<size_t>(n) * sizeof(float), static_cast<size_t>(n), sizeof(unsigned int)}));
+    int rc = alq_arena2_reserve(ctx, scratch_need({static_cast<size_t>(n) * sizeof(float), static_cast<size_t>(n), sizeof(unsigned int),
+                                                   static_cast<size_t>(c) * kBaseList * sizeof(unsigned long long),
+                                                   static_cast<size_t>(c) * sizeof(int), sizeof(int)}));
     if (rc) return rc;
     ScratchCursor cur(ctx->arena2);
     float* keys = cur.take<float>(n);
     unsigned char* taken = cur.take<unsigned char>(n);
     unsigned int* dup = cur.take<unsigned int>(1);
+    unsigned long long* cand = cur.take<unsigned long long>(static_cast<size_t>(c) * kBaseList);
+    int* fail = cur.take<int>(c);
+    int* status = cur.take<int>(1);
     ALQ_CUDA(ctx, cudaMemsetAsync(taken, 0, static_cast<size_t>(n), st));
     ALQ_CUDA(ctx, cudaMemsetAsync(dup, 0, sizeof(unsigned int), st));
     int kgrid = static_cast<int>((n + 255) / 256);
     if (kgrid > ctx->sm_count * 8) kgrid = ctx->sm_count * 8;
-    int64_t at = 0;
-    for (int cls = 0; cls < c; ++cls) {
+    // one ordinary step of the class loop (base_sampler.py:29-38) for class `cls`
+    auto class_step = [&](int cls) -> int {
         const int64_t cnt = budget / c + (cls < budget % c ? 1 : 0);      // base_sampler.py:24-25
-        if (cnt == 0) continue;
+        if (cnt == 0) return ALQ_OK;
+        const int64_t at = static_cast<int64_t>(cls) * (budget / c) + std::min<int64_t>(cls, budget % c);
         base_keys_kernel<<<kgrid, 256, 0, st>>>(min_margin, radius, ldr, pred, taken, n, cls, keys);
         ALQ_LAUNCH_CHECK(ctx);
-        rc = alq_select_smallest(ctx, keys, n, cnt, out_pos + at, stream);
-        if (rc) return rc;
+        const int r = alq_select_smallest(ctx, keys, n, cnt, out_pos + at, stream);
+        if (r) return r;
         base_mark_kernel<<<static_cast<int>((cnt + 255) / 256), 256, 0, st>>>(out_pos + at, static_cast<int>(cnt), taken, dup);
         ALQ_LAUNCH_CHECK(ctx);
-        at += cnt;
+        return ALQ_OK;
+    };
+    if (parallel) {
+        ALQ_CUDA(ctx, cudaFuncSetAttribute(base_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cand_smem)));
+        ALQ_CUDA(ctx, cudaFuncSetAttribute(base_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitset_bytes)));
+        base_candidates_kernel<<<(c + kBaseGroup - 1) / kBaseGroup, kBaseThreads, cand_smem, st>>>(
+            min_margin, radius, ldr, pred, static_cast<int>(n), c, budget, cand, fail);
+        ALQ_LAUNCH_CHECK(ctx);
+        int cls = 0, ordinary_steps = 0;
+        while (cls < c) {
+            base_resolve_kernel<<<1, kBaseThreads, bitset_bytes, st>>>(cand, fail, taken, static_cast<int>(n), c, budget, cls, out_pos, status);
+            ALQ_LAUNCH_CHECK(ctx);
+            int stopped = c;
+            ALQ_CUDA(ctx, cudaMemcpyAsync(&stopped, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+            ALQ_CUDA(ctx, cudaStreamSynchronize(st));
+            if (stopped >= c) break;
+            rc = class_step(stopped);          // a list that was too short (or not provably complete): the ordinary step
+            if (rc) return rc;
+            ++ordinary_steps;
+            cls = stopped + 1;
+        }
+        if (getenv("ALQ_BASE_DEBUG")) fprintf(stderr, "alq_base_select: %d of %d classes took the ordinary step\n", ordinary_steps, c);
+    } else {
+        for (int cls = 0; cls < c; ++cls) {
+            rc = class_step(cls);
+            if (rc) return rc;
+        }
     }
     unsigned int dup_host = 0;
     ALQ_CUDA(ctx, cudaMemcpyAsync(&dup_host, dup, sizeof(dup_host), cudaMemcpyDeviceToHost, st));

@@ -47,7 +47,8 @@ const char* alq_last_error(const alq_ctx* ctx);
 /* Implementation knobs (defaults pick the fastest valid kernel):
  *   "k3_impl"        0 auto | 1 exact-fp32 SIMT contraction | 2 tcgen05 3xTF32 contraction
  *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline
- *   "select_impl"    0 auto | 1 multi-kernel radix select   | 2 single cluster-resident launch       */
+ *   "select_impl"    0 auto | 1 multi-kernel radix select   | 2 single cluster-resident launch
+ *   "base_impl"      0 auto | 1 sequential class loop       | 2 per-class candidate lists + in-order resolve */
 int alq_set_option(alq_ctx* ctx, const char* key, int64_t value);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 int64_t alq_launch_count(const alq_ctx* ctx);
@@ -213,6 +214,8 @@ int alq_mase_margins(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, in
 /* base_sampler.py:22-38: class by class (c = 0..C-1), take the budget / C (+1 for c < budget % C) rows with the
  * smallest key  (pred[i] == c ? min_margin[i] : radius[i, c]),  rows taken by earlier classes pushed to +inf;
  * every per-class sort is K1b (stable).  out_pos[0..budget) = pool positions in pick order.  Synchronous.
+ * With many classes and <= 32 picks per class the per-class lists are extracted for all classes at once and
+ * resolved in class order on the device (same result; a class whose list runs short takes the ordinary step).
  * ALQ_ERR_NUMERIC if a row would be selected twice -- the condition the reference asserts on (:40).          */
 int alq_base_select(alq_ctx* ctx, const float* min_margin, const float* radius, int64_t ldr, const int32_t* pred,
                     int64_t n, int32_t c, int64_t budget, int32_t* out_pos, void* stream);

@@ -135,18 +135,25 @@ def test_margins_on_strided_slab_and_argmax_ties(eng):
     assert torch.equal(torch.isinf(radius.cpu()), torch.isinf(rpc))
 
 
-@pytest.mark.parametrize("n,c,budget", [(5000, 10, 333), (3000, 1000, 1500), (700, 37, 700), (90000, 100, 1000)])
+@pytest.mark.parametrize("n,c,budget", [(5000, 10, 333), (3000, 1000, 1500), (700, 37, 700), (90000, 100, 1000),
+                                        (6000, 50, 500), (20000, 1000, 10000), (4000, 1003, 3999), (300, 20, 300)])
 def test_base_select_matches_oracle(eng, n, c, budget):
+    """Sequential class loop and parallel candidate lists + in-order resolve, both against the oracle's loop."""
     torch.manual_seed(n + c)
     w = torch.randn(c, 24) * 0.3
     logits = torch.randn(n, c) * 2.0
-    if n == 5000:                                           # quantised logits: ties inside every per-class sort
+    if n in (5000, 6000):                                   # quantised logits: ties inside every per-class sort
         logits = torch.round(logits * 2) / 2
     ginv = eng.class_gap_inv(w.cuda())
     mm, pred, radius = eng.mase_margins(logits.cuda(), ginv, want_per_class=True)
-    got = eng.base_select(mm, radius, pred, budget).cpu().numpy()
     ref = O.base_select(mm.cpu(), radius.cpu(), pred.cpu().long(), budget, c)
-    assert got.tolist() == ref.tolist()                     # bit-exact: same keys, same stable tie-break
+    try:
+        for impl in (1, 2, 0):
+            eng.set_option("base_impl", impl)
+            got = eng.base_select(mm, radius, pred, budget).cpu().numpy()
+            assert got.tolist() == ref.tolist(), impl           # bit-exact: same keys, same stable tie-break
+    finally:
+        eng.set_option("base_impl", 0)
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "t", "d"])

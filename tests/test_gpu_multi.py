@@ -59,6 +59,15 @@ def _worker(rank, world, port, gold_path, out_path):
         s = make_strategy(name, lg, emb, ev, [], 64, engine=eng)
         np.random.seed(5)
         res[f"cold_{name}_single"] = [int(i) for i in s.query(12.0)[0]]
+    # MASE (rows sharded, one top-B exchange) and BASE (margins sharded + gathered, class loop replicated)
+    from helpers import HeadNet
+    mg = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_mase.npz")))
+    for tag in ("a", "b"):
+        for name, key in (("MASESampler", "mase"), ("BASESampler", "base")):
+            net = HeadNet(torch.from_numpy(mg[f"{tag}_emb"]), torch.from_numpy(mg[f"{tag}_weight"]), torch.from_numpy(mg[f"{tag}_bias"]))
+            s = make_strategy(name, None, None, mg[f"{tag}_eval"], mg[f"{tag}_labeled"], int(mg[f"{tag}_bs"]), engine=eng, net=net)
+            s._shard_group = group
+            res[f"mgold_{tag}_{key}_picks"] = [int(i) for i in s.query(float(mg[f"{tag}_budget"]))[0]]
     ranks_agree = [None] * world
     dist.all_gather_object(ranks_agree, res)
     assert all(r == res for r in ranks_agree)
@@ -77,8 +86,12 @@ def test_two_gpus_equal_reference(gold):
     mp.spawn(_worker, args=(2, port, os.path.join(ROOT, "tests", "golden", "reference_golden.npz"), out),
              nprocs=2, join=True)
     res = np.load(out, allow_pickle=True)[0]
+    mg = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_mase.npz")))
     for key, got in res.items():
         if key.startswith("cold_"):
+            continue
+        if key.startswith("mgold_"):
+            assert got == mg[key[len("mgold_"):]].tolist(), key
             continue
         assert got == gold[key].tolist(), key
     for name in ("CoresetSampler", "BADGESampler"):

@@ -353,57 +353,56 @@ base_candidates_kernel(const float* __restrict__ minm, const float* __restrict__
 
 __global__ void __launch_bounds__(kBaseThreads, 1)
 base_resolve_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ fail, unsigned char* __restrict__ taken,
-                    int n, int c, int64_t budget, int c_begin, int32_t* __restrict__ out_pos, int* __restrict__ status) {
+                    int n, int c, int64_t budget, int c_begin, int chunk, int32_t* __restrict__ out_pos, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_base[];
-    uint32_t* bits = reinterpret_cast<uint32_t*>(smem_base);
     const int words = (n + 31) / 32;
+    unsigned long long* lst = reinterpret_cast<unsigned long long*>(smem_base);            // [chunk][kBaseList]
+    int* lfail = reinterpret_cast<int*>(lst + static_cast<size_t>(chunk) * kBaseList);     // [chunk]
+    uint32_t* bits = reinterpret_cast<uint32_t*>(lfail + chunk);                           // [words]
+    __shared__ int s_stop;
     for (int w = threadIdx.x; w < words; w += kBaseThreads) {
         uint32_t v = 0;
         const int lo = w * 32, hi = min(n, lo + 32);
         for (int i = lo; i < hi; ++i) v |= (taken[i] ? 1u : 0u) << (i - lo);
         bits[w] = v;
     }
-    __syncthreads();
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+    if (threadIdx.x == 0) s_stop = -1;
+    const int lane = threadIdx.x & 31;
     const int64_t per = budget / c, extra = budget % c;
     const uint32_t ord_inf = 0xff800000u;                        // alq_ord(+inf)
-    int cls = c_begin;
-    while (cls < c && per + (cls < extra ? 1 : 0) == 0) ++cls;
-    unsigned long long e0 = kBaseEmpty, e1 = kBaseEmpty;
-    int bad = 0;
-    if (cls < c) {
-        e0 = cand[static_cast<size_t>(cls) * kBaseList + lane];
-        e1 = cand[static_cast<size_t>(cls) * kBaseList + 32 + lane];
-        bad = fail[cls];
-    }
-    int result = c;
-    while (cls < c) {
-        int nxt = cls + 1;
-        while (nxt < c && per + (nxt < extra ? 1 : 0) == 0) ++nxt;
-        unsigned long long n0 = kBaseEmpty, n1 = kBaseEmpty;     // next class's list is in flight while this one resolves
-        int nbad = 0;
-        if (nxt < c) {
-            n0 = cand[static_cast<size_t>(nxt) * kBaseList + lane];
-            n1 = cand[static_cast<size_t>(nxt) * kBaseList + 32 + lane];
-            nbad = fail[nxt];
+    for (int base = c_begin; base < c; base += chunk) {
+        // every thread stages the candidate lists of the next `chunk` classes; one warp then resolves them in order
+        const int cnt_cls = min(chunk, c - base);
+        for (int i = threadIdx.x; i < cnt_cls * kBaseList; i += kBaseThreads) lst[i] = cand[static_cast<size_t>(base) * kBaseList + i];
+        for (int i = threadIdx.x; i < cnt_cls; i += kBaseThreads) lfail[i] = fail[base + i];
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            for (int q = 0; q < cnt_cls; ++q) {
+                const int cls = base + q;
+                const int cnt = static_cast<int>(per + (cls < extra ? 1 : 0));
+                if (cnt == 0) continue;
+                const int64_t off = static_cast<int64_t>(cls) * per + min(static_cast<int64_t>(cls), extra);
+                const int len = min(cnt + 32, kBaseList);
+                const unsigned long long e0 = lst[q * kBaseList + lane], e1 = lst[q * kBaseList + 32 + lane];
+                const uint32_t r0 = static_cast<uint32_t>(e0), r1 = static_cast<uint32_t>(e1);
+                const bool v0 = lane < len && static_cast<uint32_t>(e0 >> 32) < ord_inf && !((bits[r0 >> 5] >> (r0 & 31)) & 1u);
+                const bool v1 = lane + 32 < len && static_cast<uint32_t>(e1 >> 32) < ord_inf && !((bits[r1 >> 5] >> (r1 & 31)) & 1u);
+                const uint32_t b0 = __ballot_sync(0xffffffffu, v0), b1 = __ballot_sync(0xffffffffu, v1);
+                if (lfail[q] || __popc(b0) + __popc(b1) < cnt) {          // list not provably complete, or too few free rows
+                    if (lane == 0) s_stop = cls;
+                    break;
+                }
+                const uint32_t lt = (1u << lane) - 1u;
+                const int k0 = __popc(b0 & lt), k1 = __popc(b0) + __popc(b1 & lt);
+                if (v0 && k0 < cnt) { out_pos[off + k0] = static_cast<int32_t>(r0); atomicOr(&bits[r0 >> 5], 1u << (r0 & 31)); taken[r0] = 1; }
+                if (v1 && k1 < cnt) { out_pos[off + k1] = static_cast<int32_t>(r1); atomicOr(&bits[r1 >> 5], 1u << (r1 & 31)); taken[r1] = 1; }
+                __syncwarp();
+            }
         }
-        const int cnt = static_cast<int>(per + (cls < extra ? 1 : 0));
-        const int64_t off = static_cast<int64_t>(cls) * per + min(static_cast<int64_t>(cls), extra);
-        const int len = min(cnt + 32, kBaseList);
-        const uint32_t r0 = static_cast<uint32_t>(e0), r1 = static_cast<uint32_t>(e1);
-        const bool v0 = lane < len && static_cast<uint32_t>(e0 >> 32) < ord_inf && !((bits[r0 >> 5] >> (r0 & 31)) & 1u);
-        const bool v1 = lane + 32 < len && static_cast<uint32_t>(e1 >> 32) < ord_inf && !((bits[r1 >> 5] >> (r1 & 31)) & 1u);
-        const uint32_t b0 = __ballot_sync(0xffffffffu, v0), b1 = __ballot_sync(0xffffffffu, v1);
-        if (bad || __popc(b0) + __popc(b1) < cnt) { result = cls; break; }
-        const uint32_t lt = (1u << lane) - 1u;
-        const int k0 = __popc(b0 & lt), k1 = __popc(b0) + __popc(b1 & lt);
-        if (v0 && k0 < cnt) { out_pos[off + k0] = static_cast<int32_t>(r0); atomicOr(&bits[r0 >> 5], 1u << (r0 & 31)); taken[r0] = 1; }
-        if (v1 && k1 < cnt) { out_pos[off + k1] = static_cast<int32_t>(r1); atomicOr(&bits[r1 >> 5], 1u << (r1 & 31)); taken[r1] = 1; }
-        __syncwarp();
-        cls = nxt; e0 = n0; e1 = n1; bad = nbad;
+        __syncthreads();
+        if (s_stop >= 0) break;
     }
-    if (lane == 0) *status = result;
+    if (threadIdx.x == 0) *status = s_stop >= 0 ? s_stop : c;
 }
 
 int rows_grid(const alq_ctx* ctx, int64_t n, int warps_per_block) {
@@ -504,8 +503,12 @@ extern "C" int alq_base_select(alq_ctx* ctx, const float* min_margin, const floa
     const size_t bitset_bytes = (static_cast<size_t>(n) + 31) / 32 * 4;
     const size_t cand_smem = (static_cast<size_t>(kBaseGroup) * kBaseKeep * kBaseThreads + 2 * kBaseList) * sizeof(unsigned long long);
     // many classes, few picks each: candidate lists for every class at once + an in-order resolve (base_impl: 1 = never)
+    const size_t per_class_smem = kBaseList * sizeof(unsigned long long) + sizeof(int);
     const bool parallel = ctx->base_impl != 1 && cnt_max <= kBaseMaxCnt && (c >= 16 || ctx->base_impl == 2) &&
-                          bitset_bytes + 1024 <= ctx->smem_optin && cand_smem + 1024 <= ctx->smem_optin;
+                          bitset_bytes + 8 * per_class_smem + 1024 <= ctx->smem_optin && cand_smem + 1024 <= ctx->smem_optin;
+    // the resolve kernel stages `chunk` candidate lists at a time next to its bitset of taken rows
+    const int chunk = parallel ? static_cast<int>(std::min<size_t>(256, (ctx->smem_optin - 1024 - bitset_bytes) / per_class_smem)) : 0;
+    const size_t resolve_smem = chunk * per_class_smem + bitset_bytes;
     // private arena: alq_select_smallest re-carves the shared scratch on every call
     int rc = alq_arena2_reserve(ctx, scratch_need({static_cast<size_t>(n) * sizeof(float), static_cast<size_t>(n), sizeof(unsigned int),
                                                    static_cast<size_t>(c) * kBaseList * sizeof(unsigned long long),
@@ -537,13 +540,13 @@ extern "C" int alq_base_select(alq_ctx* ctx, const float* min_margin, const floa
     };
     if (parallel) {
         ALQ_CUDA(ctx, cudaFuncSetAttribute(base_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cand_smem)));
-        ALQ_CUDA(ctx, cudaFuncSetAttribute(base_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bitset_bytes)));
+        ALQ_CUDA(ctx, cudaFuncSetAttribute(base_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(resolve_smem)));
         base_candidates_kernel<<<(c + kBaseGroup - 1) / kBaseGroup, kBaseThreads, cand_smem, st>>>(
             min_margin, radius, ldr, pred, static_cast<int>(n), c, budget, cand, fail);
         ALQ_LAUNCH_CHECK(ctx);
         int cls = 0, ordinary_steps = 0;
         while (cls < c) {
-            base_resolve_kernel<<<1, kBaseThreads, bitset_bytes, st>>>(cand, fail, taken, static_cast<int>(n), c, budget, cls, out_pos, status);
+            base_resolve_kernel<<<1, kBaseThreads, resolve_smem, st>>>(cand, fail, taken, static_cast<int>(n), c, budget, cls, chunk, out_pos, status);
             ALQ_LAUNCH_CHECK(ctx);
             int stopped = c;
             ALQ_CUDA(ctx, cudaMemcpyAsync(&stopped, status, sizeof(int), cudaMemcpyDeviceToHost, st));

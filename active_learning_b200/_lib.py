@@ -81,6 +81,7 @@ SIGNATURES = {
                                C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "alq_argmin": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_i32p, C.c_void_p]),
     "alq_greedy_select": (C.c_int, [C.c_void_p, C.POINTER(GreedyDesc), C.c_void_p]),
+    "alq_ratio_argmin": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int64, c_i32p, C.c_void_p]),
     "alq_class_gap_inv": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int64, c_f32p, C.c_int64,
                                     c_f32p, C.c_void_p]),
     "alq_mase_margins": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64, c_f32p, C.c_int64,

@@ -199,6 +199,37 @@ __global__ void __launch_bounds__(1024) argmin_kernel(const float* __restrict__ 
     }
 }
 
+// balancing_sampler.py:114-119: arg-min of num[i] / den[i] over the rows with avail[i] != 0, lowest index among equal
+// ratios (torch's CPU min over the compacted vector).  num == nullptr: the numerator is the constant 1 (:104-107).
+__global__ void __launch_bounds__(1024) ratio_argmin_kernel(const float* __restrict__ num, const float* __restrict__ den,
+                                                            const unsigned char* __restrict__ avail, int64_t n,
+                                                            int32_t* out) {
+    __shared__ unsigned long long sm[32];
+    unsigned long long best = ~0ull;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!avail[i]) continue;
+        const float r = __fdiv_rn(num ? num[i] : 1.0f, den[i]);
+        const unsigned long long k = (static_cast<unsigned long long>(alq_ord(r + 0.0f)) << 32) | static_cast<uint32_t>(i);
+        best = k < best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, best, o);
+        best = w < best ? w : best;
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = sm[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long w = __shfl_xor_sync(0xffffffffu, best, o);
+            best = w < best ? w : best;
+        }
+        if (threadIdx.x == 0) out[0] = best == ~0ull ? -1 : static_cast<int32_t>(best & 0xffffffffu);
+    }
+}
+
 }  // namespace
 
 int alq_min_dist_tc(alq_ctx* ctx, const float* x, int64_t ldx, const float* xn, int64_t n, const float* y,
@@ -260,6 +291,15 @@ extern "C" int alq_min_dist(alq_ctx* ctx, const float* x, int64_t ldx, const flo
         if (reduce_max) min_dist_kernel<false, true><<<grid, kThreads, 0, st>>>(X, xn, Y, yn, d, XA, xan, YA, yan, c, per, out);
         else min_dist_kernel<false, false><<<grid, kThreads, 0, st>>>(X, xn, Y, yn, d, XA, xan, YA, yan, c, per, out);
     }
+    ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}
+
+extern "C" int alq_ratio_argmin(alq_ctx* ctx, const float* num, const float* den, const unsigned char* avail, int64_t n,
+                                int32_t* out_row, void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (n <= 0 || n >= (1LL << 31) || !den || !avail || !out_row) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_ratio_argmin: bad arguments");
+    ratio_argmin_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(num, den, avail, n, out_row);
     ALQ_LAUNCH_CHECK(ctx);
     return ALQ_OK;
 }

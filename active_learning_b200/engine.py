@@ -213,6 +213,18 @@ class Engine:
                     "alq_argmin")
         return int(out.item())
 
+    def ratio_argmin(self, num: Optional[torch.Tensor], den: torch.Tensor, avail: torch.Tensor) -> int:
+        """argmin of num / den over rows with avail != 0 (num None = 1): balancing_sampler.py:114-119."""
+        den = _f32c(den, "den")
+        if num is not None:
+            num = _f32c(num, "num")
+        if avail.dtype != torch.uint8 or not avail.is_cuda or avail.numel() != den.numel():
+            raise AlqError("ratio_argmin: avail must be a CUDA uint8 tensor with one entry per row")
+        out = torch.empty(1, dtype=torch.int32, device=den.device)
+        self._check(self.lib.alq_ratio_argmin(self._h, _ptr(num), _ptr(den), _ptr(avail.contiguous()), den.numel(), _ptr(out),
+                                              self._stream()), "alq_ratio_argmin")
+        return int(out.item())
+
     # -- K6: MASE / BASE ---------------------------------------------------------------------------------
     def class_gap_inv(self, weight: torch.Tensor):
         """Head geometry of the linear classifier: (ginv [c, c padded to x4], gmin [c + 1]) with

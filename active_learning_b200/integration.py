@@ -15,6 +15,7 @@ from __future__ import annotations
 
 from .query_strategies.coreset import (BADGEQuery, CoresetQuery, PartitionedBADGEQuery,
                                        PartitionedCoresetQuery)
+from .query_strategies.balancing import BalancingQuery
 from .query_strategies.mase import BASEQuery, MASEQuery
 from .query_strategies.uncertainty import ConfidenceQuery, EntropyQuery, MarginQuery
 
@@ -28,6 +29,7 @@ _MIXINS = {
     "PartitionedBADGESampler": PartitionedBADGEQuery,
     "MASESampler": MASEQuery,
     "BASESampler": BASEQuery,
+    "BalancingSampler": BalancingQuery,
 }
 
 

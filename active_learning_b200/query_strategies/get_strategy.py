@@ -1,8 +1,9 @@
 """`--strategy` dispatch, same contract as /root/reference/src/query_strategies/get_strategy.py:
-`get_strategy(name)` returns the class called `name`.  The nine accelerated samplers (the seven of the
-north-star path plus MASE / BASE) and the default RandomSampler are implemented; the reference's remaining class names resolve to a
+`get_strategy(name)` returns the class called `name`.  The ten accelerated samplers (the seven of the
+north-star path plus MASE / BASE / Balancing) and the default RandomSampler are implemented; the reference's remaining class names resolve to a
 stub that raises a clear error (out of scope for this path)."""
 from .badge_sampler import BADGESampler  # noqa: F401
+from .balancing_sampler import BalancingSampler  # noqa: F401
 from .base_sampler import BASESampler  # noqa: F401
 from .confidence_sampler import ConfidenceSampler  # noqa: F401
 from .coreset_sampler import CoresetSampler  # noqa: F401
@@ -14,8 +15,9 @@ from .partitioned_coreset_sampler import PartitionedCoresetSampler  # noqa: F401
 from .random_sampler import RandomSampler  # noqa: F401
 
 ACCELERATED = ("MarginSampler", "ConfidenceSampler", "EntropySampler", "CoresetSampler",
-               "PartitionedCoresetSampler", "BADGESampler", "PartitionedBADGESampler", "MASESampler", "BASESampler")
-NOT_ON_THIS_PATH = ("BalancedRandomSampler", "BalancingSampler", "MarginClusteringSampler", "VAALSampler")
+               "PartitionedCoresetSampler", "BADGESampler", "PartitionedBADGESampler", "MASESampler", "BASESampler",
+               "BalancingSampler")
+NOT_ON_THIS_PATH = ("BalancedRandomSampler", "MarginClusteringSampler", "VAALSampler")
 
 
 def _out_of_scope(name):

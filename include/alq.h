@@ -139,6 +139,13 @@ int alq_min_dist(alq_ctx* ctx,
 /* out_row[0] = argmin_i v[i] (lowest index on ties) -- second half of coreset_sampler.py:100. */
 int alq_argmin(alq_ctx* ctx, const float* v, int64_t n, int32_t* out_row, void* stream);
 
+/* balancing_sampler.py:114-119: out_row[0] = argmin_i num[i] / den[i] over the rows with avail[i] != 0 (lowest index on
+ * ties; -1 if no row is available).  num == NULL stands for the constant 1 (the rarest class has no labeled row,
+ * :104-107).  num / den are K3 outputs: squared distance to the rarest class centre / largest squared distance to a
+ * majority class centre (alq_min_dist with reduce_max).                                                        */
+int alq_ratio_argmin(alq_ctx* ctx, const float* num, const float* den, const unsigned char* avail, int64_t n,
+                     int32_t* out_row, void* stream);
+
 /* ---- K4 / K5: greedy k-center and k-means++ D^2 seeding ----------------------------------------
  * Replaces the step loop of coreset_sampler.py:77-103.  Candidates are the UNLABELED rows only;
  * `mind` arrives holding their min squared distance to the labeled set (K3; +inf if none) and is

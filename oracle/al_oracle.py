@@ -12,7 +12,8 @@ own code (imported in the build container from /root/reference/src with a comet_
 and ``tests/test_oracle_golden.py`` replays them.  The one exception is ``entropy`` scoring:
 the reference has no EntropySampler (SURVEY.md finding 1), so that mode is *parity unpinned*
 and its spec is defined here.  The MASE / BASE functions at the end
-are pinned the same way by ``tests/golden/make_golden_mase.py``.
+are pinned the same way by ``tests/golden/make_golden_mase.py``, ``balancing_query`` by
+``tests/golden/make_golden_balancing.py``.
 
 All citations are relative to /root/reference/src/query_strategies/.
 """
@@ -410,3 +411,62 @@ def base_select(min_margins: torch.Tensor, per_class_margins: torch.Tensor, pred
         picked += select_smallest(key, count).tolist()
     assert len(picked) == len(set(picked))
     return np.asarray(picked, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------------------
+# BalancingSampler  (balancing_sampler.py:26-134)
+# --------------------------------------------------------------------------------------
+def balancing_query(embeddings: torch.Tensor, ys: torch.Tensor, idxs_for_query: np.ndarray, idxs_labeled: np.ndarray,
+                    budget, num_classes: int, diag: dict | None = None):
+    """balancing_sampler.py:58-134, one pick per step: if the labeled class histogram is imbalanced relative to the
+    remaining budget (:81-82), take the available row that minimises
+        d2(row, centre of the rarest class) / max_{majority classes} d2(row, centre)      (:95-120, first index on ties),
+    with class centres = mean labeled embedding (count + 1e-5 in the denominator, :86-88) and numerator 1 when the
+    rarest class has no labeled row (:104-107); otherwise one `np.random.choice` over the available rows (:124).
+    `idxs_for_query` / `idxs_labeled` are boolean masks over the pool and are updated like the reference's (:127-128).
+    `diag["min_rel_gap"]` receives the smallest relative gap between the two smallest ratios of any balancing step."""
+    embeddings = embeddings.detach().to(torch.float32).cpu()
+    ys = ys.detach().cpu()
+    idxs_for_query = np.array(idxs_for_query, dtype=bool)
+    idxs_labeled = np.array(idxs_labeled, dtype=bool)
+    budget = int(min(idxs_for_query.sum(), budget))
+    picks, gap, n_bal = [], float("inf"), 0
+    for query_count in range(budget):
+        ys_labeled = ys[idxs_labeled]
+        count = (ys_labeled[None, :] == torch.arange(num_classes)[:, None]).sum(dim=1)             # :66-67
+        labeled_count = idxs_labeled.sum()
+        mean_count = count.float().mean()
+        maj = count > mean_count                                                                    # :71
+        maj_avg = count[maj].sum() / maj.sum()
+        minor = count <= mean_count
+        minor_avg = count[minor].sum() / minor.sum()
+        if budget - query_count <= minor.sum() * (maj_avg - minor_avg):                             # :81-82
+            emb_l = embeddings[idxs_labeled]
+            avg = torch.zeros(num_classes, labeled_count)                                           # :86-88
+            avg[ys_labeled, torch.arange(len(ys_labeled))] = 1
+            avg = avg / (avg.sum(dim=1, keepdims=True) + 1e-5)
+            centres = avg @ emb_l
+            c_major = centres[maj]
+            rare_count, rare = count.min(dim=0)
+            c_rare = centres[rare][None, :]
+            emb_u = embeddings[idxs_for_query]
+            a2 = emb_u.square().sum(dim=1, keepdims=True)
+            d_rare = a2 + c_rare.square().sum(dim=1, keepdims=True).T - 2 * (emb_u @ c_rare.T)      # :98-101
+            if rare_count == 0:
+                d_rare = torch.ones_like(d_rare)
+            d_major = a2 + c_major.square().sum(dim=1, keepdims=True).T - 2 * (emb_u @ c_major.T)   # :109-112
+            ratio = (d_rare / d_major.max(dim=1, keepdims=True).values).squeeze()                   # :114-117
+            q_in = ratio.min(dim=0).indices
+            query_idx = np.where(idxs_for_query)[0][q_in]
+            if ratio.numel() > 1:
+                two = torch.topk(ratio.double().reshape(-1), 2, largest=False).values
+                gap = min(gap, float((two[1] - two[0]) / two[1].abs().clamp_min(1e-30)))
+            n_bal += 1
+        else:
+            query_idx = np.random.choice(np.where(idxs_for_query.squeeze())[0])                     # :124
+        idxs_for_query[query_idx] = False
+        idxs_labeled[query_idx] = True
+        picks.append(int(query_idx))
+    if diag is not None:
+        diag["min_rel_gap"], diag["balancing_steps"] = gap, n_bal
+    return picks, len(picks)

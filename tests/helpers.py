@@ -24,6 +24,20 @@ class IndexDataset(torch.utils.data.Dataset):
         return torch.tensor(float(i)), 0, i
 
 
+class LabeledIndexDataset(torch.utils.data.Dataset):
+    """Pool stand-in whose labels matter (BalancingSampler reads y from the loader)."""
+
+    def __init__(self, ys, num_classes):
+        self.ys, self.num_classes = [int(v) for v in ys], num_classes
+        self.targets = self.ys
+
+    def __len__(self):
+        return len(self.ys)
+
+    def __getitem__(self, i):
+        return torch.tensor(float(i)), self.ys[i], i
+
+
 class LookupNet(nn.Module):
     """net(x) -> logits[x];  net(x, return_features=...) -> (logits[x], emb[x])."""
 
@@ -71,14 +85,14 @@ class FakeExperiment:
         return lambda *a, **k: None
 
 
-def make_strategy(name, logits, emb, eval_idxs, labeled, batch_size, engine=None, net=None, **kw):
+def make_strategy(name, logits, emb, eval_idxs, labeled, batch_size, engine=None, net=None, dataset=None, **kw):
     from active_learning_b200.query_strategies.get_strategy import get_strategy
     if net is None:
         n, c = logits.shape
         net = LookupNet(logits, emb)
     else:                                   # a HeadNet: logits come out of its own linear head
         n, c = net.emb.shape[0], net.linear.out_features
-    ds = IndexDataset(n, c)
+    ds = IndexDataset(n, c) if dataset is None else dataset
     args = dict(early_stop_patience=0, n_epoch=1, world_size=1, model="SSLResNet18",
                 freeze_feature=True, ckpt_path=tempfile.mkdtemp(prefix="alq_test_"), exp_name="t",
                 subset_labeled=None, subset_unlabeled=None, partitions=1)
@@ -153,6 +167,11 @@ class OracleEngine:
 
     def argmin(self, v):
         return int(v.min(dim=0).indices.item())
+
+    def ratio_argmin(self, num, den, avail):
+        r = (torch.ones_like(den) if num is None else num) / den
+        r = torch.where(avail.bool(), r, torch.tensor(float("inf")))
+        return int(r.min(dim=0).indices)
 
     def class_gap_inv(self, weight):
         w = weight.detach().float()

@@ -86,13 +86,15 @@ class Strategy:
         return lab
 
     def update(self, labeled_idxs, cur_cost):
-        """strategy.py:459-485 (same assertion, same artefact file)."""
+        """strategy.py:459-485 (same assertion, same artefact file).  The reference walks the B new indices in a Python
+        loop (:468-471); the check and the mask update are vectorised here: an index that is
+        already labeled, or that appears twice in the list, trips the same assertion."""
         if isinstance(labeled_idxs, list):
             labeled_idxs = np.array(labeled_idxs)
         self.idxs_lb_recent = labeled_idxs
-        for idx in self.idxs_lb_recent:
-            assert self.idxs_lb[int(idx)] == False  # noqa: E712  never re-label
-            self.idxs_lb[int(idx)] = True
+        idx = np.asarray(labeled_idxs).reshape(-1).astype(np.int64)
+        assert not self.idxs_lb[idx].any() and len(np.unique(idx)) == len(idx)   # never re-label (:470)
+        self.idxs_lb[idx] = True
         self.cumulative_cost += cur_cost
         exp = self.comet_experiment
         if exp is not None:

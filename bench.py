@@ -142,6 +142,38 @@ def cpu_margin_tail(logits, budget):
     return O.select_smallest(scores, budget)
 
 
+def cpu_greedy_baseline(steps=20):
+    """the reference's own CoreSet / k-means++ selection on the host cores -- the oracle port of
+    coreset_sampler.py:59-105 on ONE partition of the paper's configuration (gen_jobs.py:11-13: 13 000 rows = 5 000
+    labeled + 8 000 unlabeled), `steps` steps of each mode, extrapolated linearly to 10 partitions x 1 000 picks (the
+    per-step cost grows with the labeled set, so the extrapolation favours the CPU).  The non-partitioned 130 000-row
+    query the GPU workloads run needs a 67.6 GB distance matrix and cannot be run by the reference at all."""
+    from oracle import al_oracle as O
+    threads = host_cpu_budget()
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(5)
+    rows, lab, parts, picks = 13000, 5000, 10, 1000
+    ind = np.zeros(rows, dtype=bool)
+    ind[:lab] = True
+    out = {"unit": "samples/s", "kind": "port", "cores": threads, "extrapolated": True,
+           "sample": f"one partition of {rows} rows ({lab} labeled), pairwise matrix + {steps} steps per mode of the oracle port "
+                     f"of coreset_sampler.py:59-105, scaled to {parts} partitions x {picks} picks; {cpu_model()}"}
+    for kind, dim, randomize in (("coreset", EMB_DIM, False), ("badge", 512, True)):
+        feat = torch.relu(torch.randn(rows, dim, generator=g))
+        t0 = time.perf_counter()
+        dist = O.pairwise_l2_dist(feat)
+        t_pair = time.perf_counter() - t0
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        O.coreset(dist, ind, steps, randomize=randomize)
+        t_step = (time.perf_counter() - t0) / steps
+        del dist
+        round_s = parts * (t_pair + picks * t_step)
+        out[kind] = {"value": N_ROWS / round_s, "seconds_per_round": round_s, "pairwise_s": t_pair, "step_ms": t_step * 1e3,
+                     "dim": dim}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -653,6 +685,13 @@ def run_own(args):
             extras["mase_base"] = {"error": repr(exc)}
         torch.cuda.empty_cache()
         if world == 1:
+            try:
+                cpu = cpu_greedy_baseline()
+                for kind in ("coreset", "badge"):
+                    if "error" not in extras.get(kind, {"error": 1}):
+                        extras[kind]["cpu_baseline"] = dict({k: v for k, v in cpu.items() if k not in ("coreset", "badge")}, **cpu[kind])
+            except Exception as exc:  # report, never hide
+                extras["cpu_greedy_baseline_error"] = repr(exc)
             try:
                 extras["pool_forward_e2e"] = run_pool_forward_workload(eng)
             except Exception as exc:  # report, never hide

@@ -283,3 +283,19 @@ def test_mase_self_check_catches_a_wrong_head(mgold):
     s.net.forward = skewed
     with pytest.raises(AssertionError):
         s.query(10.0)
+
+
+def test_update_is_vectorised_with_the_reference_assertion(gold):
+    """strategy.py:468-471: labeling an index twice (already labeled, or repeated in the list) asserts."""
+    n, ev, lab = _pool(gold)
+    s = make_strategy("RandomSampler", torch.zeros(n, 10), torch.zeros(n, 4), ev, lab, 64)
+    assert s.idxs_lb.sum() == len(lab) and s.cumulative_cost == len(lab)
+    free = np.setdiff1d(np.arange(n), lab)[:5]
+    s.update(free.tolist(), 5)                                  # list input (main_al.py:158 passes query()'s list)
+    assert s.idxs_lb[free].all() and s.cumulative_cost == len(lab) + 5
+    with pytest.raises(AssertionError):
+        s.update(np.array([free[0]]), 1)                        # already labeled
+    other = np.setdiff1d(np.arange(n), np.flatnonzero(s.idxs_lb))[:2]
+    with pytest.raises(AssertionError):
+        s.update(np.array([other[0], other[1], other[0]]), 3)   # repeated inside one call
+    s.update(np.array([], dtype=np.int64), 0)                   # empty round

@@ -55,33 +55,34 @@ class BalancingQuery(EngineMixin):
             sums.index_add_(0, ys_dev[lab_rows], emb[lab_rows])
         xn = eng.row_norm2(emb)
         avail = torch.from_numpy(idxs_for_query.astype(np.uint8)).to(dev)
-        ys_labeled_count = torch.bincount(ys[torch.from_numpy(idxs_labeled)], minlength=C)[:C]      # (C,) int64, :66-67
-        query_count = 0
-        for _ in range(budget):
-            mean_labeled_count = ys_labeled_count.float().mean()
-            maj_classes = ys_labeled_count > mean_labeled_count
-            maj_classes_avgcount = ys_labeled_count[maj_classes].sum() / maj_classes.sum()
-            minor_classes = ys_labeled_count <= mean_labeled_count
-            minor_classes_avgcount = ys_labeled_count[minor_classes].sum() / minor_classes.sum()
-            if budget - query_count <= minor_classes.sum() * (maj_classes_avgcount - minor_classes_avgcount):   # :81-82
-                rarest_class_count, rarest_class = ys_labeled_count.min(dim=0)
-                rows = torch.cat([rarest_class.reshape(1), torch.nonzero(maj_classes).reshape(-1)]).to(dev)
-                denom = ys_labeled_count.to(torch.float32).to(dev)[rows] + 1e-5                      # :88
-                centres = sums[rows] / denom[:, None]
+        hist = torch.bincount(ys[torch.from_numpy(idxs_labeled)], minlength=C)[:C]     # labeled rows per class (int64)
+        for step in range(budget):
+            majority = self._needs_balancing(hist, budget - step)
+            if majority is not None:
+                rare_n, rare = hist.min(dim=0)                                       # first index among the rarest
+                rows = torch.cat([rare.reshape(1), torch.nonzero(majority).reshape(-1)]).to(dev)
+                centres = sums[rows] / (hist.to(torch.float32).to(dev)[rows] + 1e-5)[:, None]      # :86-88
                 cn = eng.row_norm2(centres)
-                d_major = eng.min_dist(emb, xn, centres[1:], cn[1:], reduce_max=True)               # :109-114
-                d_rare = None
-                if rarest_class_count != 0:                                                          # :104-107
-                    d_rare = eng.min_dist(emb, xn, centres[:1], cn[:1])                              # :98-101
-                query_idx = np.int64(eng.ratio_argmin(d_rare, d_major, avail))                       # :115-121
+                far = eng.min_dist(emb, xn, centres[1:], cn[1:], reduce_max=True)    # largest d2 to a majority centre
+                near = eng.min_dist(emb, xn, centres[:1], cn[:1]) if rare_n != 0 else None   # :104-107: numerator 1
+                pick = np.int64(eng.ratio_argmin(near, far, avail))                  # :115-121
             else:
-                query_idx = np.random.choice(np.where(idxs_for_query.squeeze() == True)[0])          # noqa: E712  :124
-            idxs_for_query[query_idx] = False
-            idxs_labeled[query_idx] = True
-            labeled_idxs_cur_rd.append(query_idx)
-            query_count += 1
-            cls = int(ys[int(query_idx)])
-            ys_labeled_count[cls] += 1
-            sums[cls] += emb[int(query_idx)]
-            avail[int(query_idx)] = 0
-        return labeled_idxs_cur_rd, query_count
+                pick = np.random.choice(np.where(idxs_for_query.squeeze() == True)[0])   # noqa: E712  :124
+            idxs_for_query[pick] = False
+            idxs_labeled[pick] = True
+            labeled_idxs_cur_rd.append(pick)
+            cls = int(ys[int(pick)])
+            hist[cls] += 1
+            sums[cls] += emb[int(pick)]
+            avail[int(pick)] = 0
+        return labeled_idxs_cur_rd, len(labeled_idxs_cur_rd)
+
+    @staticmethod
+    def _needs_balancing(hist, remaining):
+        """The imbalance test of balancing_sampler.py:66-82 on the labeled-class histogram, evaluated with the same
+        torch-CPU promotions (int64 counts against their fp32 mean, true division of the sums).  Returns the boolean
+        mask of the majority classes if the step must balance, None if it draws at random."""
+        mean = hist.float().mean()
+        above, rest = hist > mean, hist <= mean
+        spread = hist[above].sum() / above.sum() - hist[rest].sum() / rest.sum()     # NaN when no class is above
+        return above if bool(remaining <= rest.sum() * spread) else None

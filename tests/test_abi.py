@@ -48,3 +48,39 @@ def test_create_without_gpu_fails_cleanly():
     lib = _lib.load()
     h = ctypes.c_void_p()
     assert lib.alq_create(ctypes.byref(h), 0) != 0 and not h.value
+
+
+def _header_prototypes():
+    src = open(os.path.join(ROOT, "include", "alq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int64_t|int|void|const char\*)\s+(alq_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        args = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        protos[name] = (ret, args)
+    return protos
+
+
+def test_ctypes_argument_lists_match_the_header_prototypes():
+    """Every parameter of every prototype: pointer vs 32-bit vs 64-bit integer must agree with the ctypes argtypes
+    (a drifted binding would pass garbage without any error)."""
+    from active_learning_b200 import _lib
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def kind_of_c(decl):
+        if "*" in decl:
+            return "ptr"
+        t = decl.split()[-2] if len(decl.split()) > 1 else decl
+        return {"int64_t": "i64", "int32_t": "i32", "int": "i32", "size_t": "i64"}[t]
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_int64, ctypes.c_size_t):
+            return "i64"
+        if t in (ctypes.c_int32, ctypes.c_int):
+            return "i32"
+        return "ptr"                                   # c_void_p, c_char_p, POINTER(...)
+
+    for name, (ret, args) in protos.items():
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert [kind_of_c(a) for a in args] == [kind_of_ctypes(t) for t in argtypes], name
+        assert (restype is None) == (ret == "void"), name

@@ -268,6 +268,10 @@ def test_mase_base_plumbing(mgold, tag):
     assert mm.shape == (len(pool),) and pc.shape == (len(pool), s.num_classes)
     assert pred.dtype == torch.int64 and len(true) == len(pool)
     torch.testing.assert_close(mm, torch.from_numpy(g[f"{tag}_min_margins"]), rtol=1e-4, atol=2e-6)
+    # mase_sampler.py:30-33: the augmented train_set can stand in for al_set (same object in this harness)
+    mm_aug, _, pred_aug, _ = s.compute_margins(pool, use_training_augmentation=True)
+    assert torch.equal(mm_aug, mm) and torch.equal(pred_aug, pred)
+    assert s.query(0.0) == ([], 0)
 
 
 def test_mase_self_check_catches_a_wrong_head(mgold):

@@ -16,7 +16,7 @@ ALQ_OK = 0
 ERR_NAMES = {1: "ALQ_ERR_INVALID", 2: "ALQ_ERR_CUDA", 3: "ALQ_ERR_NOMEM", 4: "ALQ_ERR_STATE",
              5: "ALQ_ERR_NUMERIC"}
 MODE_MARGIN, MODE_LEAST_CONFIDENCE, MODE_ENTROPY = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_f32p = C.c_void_p
 c_i32p = C.c_void_p
@@ -42,7 +42,7 @@ class GreedyDesc(C.Structure):
         ("picks", C.c_void_p),
         ("variant", C.c_int32),
         ("shard_off_host", C.c_void_p),
-        ("vpos_all", C.c_void_p),
+        ("shard_pos_host", C.c_void_p),
         ("step_kernel_ms_host", C.c_void_p),
     ]
 
@@ -81,6 +81,7 @@ SIGNATURES = {
                                C.c_int32, C.c_int32, c_f32p, C.c_void_p]),
     "alq_argmin": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, c_i32p, C.c_void_p]),
     "alq_greedy_select": (C.c_int, [C.c_void_p, C.POINTER(GreedyDesc), C.c_void_p]),
+    "alq_pairwise_leaf_bounds": (C.c_int64, [C.c_int64, c_i32p, C.c_int64]),
     "alq_ratio_argmin": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, C.c_int64, c_i32p, C.c_void_p]),
     "alq_class_gap_inv": (C.c_int, [C.c_void_p, c_f32p, C.c_int32, C.c_int32, C.c_int64, c_f32p, C.c_int64,
                                     c_f32p, C.c_void_p]),

@@ -4,7 +4,7 @@
 
 #include "alq_common.cuh"
 
-extern "C" int alq_version(void) { return 4; }
+extern "C" int alq_version(void) { return 5; }
 
 extern "C" int alq_create(alq_ctx** out, int device) {
     if (!out) return ALQ_ERR_INVALID;
@@ -59,7 +59,8 @@ extern "C" int alq_set_option(alq_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return ALQ_ERR_INVALID;
     const std::string k(key);
     if (k == "k3_impl" && value >= 0 && value <= 2) ctx->k3_impl = static_cast<int>(value);
-    else if (k == "greedy_variant" && value >= 0 && value <= 2) ctx->greedy_variant = static_cast<int>(value);
+    else if (k == "greedy_variant" && value >= 0 && value <= 3) ctx->greedy_variant = static_cast<int>(value);
+    else if (k == "spin_timeout_ms" && value >= 1 && value <= 3600000) ctx->spin_timeout_ms = static_cast<int>(value);
     else if (k == "select_impl" && value >= 0 && value <= 2) ctx->select_impl = static_cast<int>(value);
     else if (k == "base_impl" && value >= 0 && value <= 2) ctx->base_impl = static_cast<int>(value);
     else ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_set_option: unknown option or value: %s=%lld", key, (long long)value);

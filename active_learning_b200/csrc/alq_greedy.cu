@@ -19,44 +19,13 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "alq_common.cuh"
+#include "alq_greedy.cuh"
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------
 // shared argument blocks
 // ------------------------------------------------------------------------------------------------
-struct BlockSeg {        // one CTA's share of the rows
-    int row_lo, row_hi, part, pad;
-};
-
-// ---- multi-GPU exchange through peer-memory windows (alq_comm.cu) --------------------------------
-// Every rank owns a window that its peers write into with plain stores over NVLink; consumers spin on
-// epoch-tagged 64-bit flags with ld.acquire.sys.  Window layout (identical on every rank):
-//   ready [world]                     u64   "rank r has initialised its window for this call"
-//   slot  [RING][world]               {u64 key, u64 flag, float payload[...]}      arg-max: local winners
-//   mflag [RING][world]               u64   "rank r's min-distances of step t are in your replica"
-//   cflag [RING]                      u64   "the centre row of step t is in centre[t % RING]"
-//   centre[RING]                      float payload[...]                           D^2: owner pushes the row
-//   mfull [2][full_n padded]          float running min-distances, replicated, double buffered by parity
-// payload = [x row (d)] [a row (c)] [|x|^2] [|a|^2], padded to x4 floats.
-constexpr int kRing = 4;
-
-struct CommArgs {
-    int world, rank;
-    int row_base;                      // global row id of this rank's row 0
-    int n_global;
-    unsigned long long tag;            // epoch << 32
-    char* peer[ALQ_MAX_WORLD];         // mapped windows; peer[rank] is the local one
-    int shard_off[ALQ_MAX_WORLD + 1];
-    size_t ready_off, slot_off, slot_bytes, mflag_off, cflag_off, centre_off, centre_bytes, mfull_off[2];
-    int payload_floats;
-};
-
-__device__ __forceinline__ char* slot_ptr(const CommArgs& cm, int peer, int ring, int src) {
-    return cm.peer[peer] + cm.slot_off + (static_cast<size_t>(ring) * cm.world + src) * cm.slot_bytes;
-}
-
 struct StepArgs {
     const float* x;  int64_t ldx; int d;
     const float* a;  int64_t lda; int c;
@@ -71,15 +40,9 @@ struct StepArgs {
     const int* vpos;                // [n]
     float* cfull;                   // concatenated per-partition full arrays
     const int* cfull_off;           // [P]
-    CommArgs cm;                    // world == 1: single GPU
-    unsigned int* ticket;           // [bmax + 1] last-CTA election per step (multi-GPU)
     int* status;
     int* picks;
 };
-
-__device__ __forceinline__ float dist_dense(float n_i, float n_q, float dot) {
-    return (n_i + n_q) - 2.0f * dot;
-}
 
 // final per-row bookkeeping, executed by one lane
 template <bool SAMPLE>
@@ -89,125 +52,31 @@ __device__ __forceinline__ void finish_row(const StepArgs& A, int row, int centr
     if (row == centre) m = ALQ_NEG_INF;   // a picked row is never a candidate again
     A.mind[row] = m;
     if (SAMPLE) {
-        if (A.cm.world == 1) {
-            A.cfull[cf_off + A.vpos[row]] = m;      // raw running min; the sampling stage clips at 0
-        } else {                                    // every rank keeps a replica: store to all windows (NVLink)
-            const int vp = A.vpos[row];
-            for (int g = 0; g < A.cm.world; ++g)
-                reinterpret_cast<float*>(A.cm.peer[g] + A.cm.mfull_off[A.t & 1])[vp] = m;
-        }
+        A.cfull[cf_off + A.vpos[row]] = m;          // raw running min; the sampling stage clips at 0
     } else {
-        const unsigned long long k = alq_maxkey(m, static_cast<uint32_t>(A.cm.row_base + row));   // global row id
+        const unsigned long long k = alq_maxkey(m, static_cast<uint32_t>(row));
         best_key = k > best_key ? k : best_key;
     }
 }
 
-// ---- centre of this step: single GPU reads it from its own rows; multi-GPU takes the payload a peer
-//      (or this rank) pushed into the local window.  Called by every thread of the CTA, followed by
+// ---- centre of this step, read from the candidate rows.  Called by every thread of the CTA, followed by
 //      __syncthreads() in the caller.
 struct CentreInfo { int local; float qn; };
 
 template <bool FACTORED, bool SAMPLE>
-__device__ __forceinline__ CentreInfo load_centre(const StepArgs& A, int part, float* sq, int* sh_i) {
+__device__ __forceinline__ CentreInfo load_centre(const StepArgs& A, int part, float* sq) {
     const int dv = A.d >> 2, cv = FACTORED ? (A.c >> 2) : 0;
     float4* dst = reinterpret_cast<float4*>(sq);
-    if (A.cm.world == 1) {
-        const int centre = SAMPLE ? A.cur[part]
-                                  : static_cast<int>(alq_maxkey_row(__ldcg(&A.best[static_cast<size_t>(A.t - 1) * A.P + part])));
-        const float4* src = reinterpret_cast<const float4*>(A.x + static_cast<int64_t>(centre) * A.ldx);
-        for (int k = threadIdx.x; k < dv; k += blockDim.x) dst[k] = src[k];
-        if (FACTORED) {
-            const float4* sa = reinterpret_cast<const float4*>(A.a + static_cast<int64_t>(centre) * A.lda);
-            for (int k = threadIdx.x; k < cv; k += blockDim.x) dst[dv + k] = sa[k];
-        }
-        return CentreInfo{centre, FACTORED ? A.xn[centre] * A.an[centre] : A.xn[centre]};
-    }
-    const CommArgs& cm = A.cm;
-    const int ring = (A.t - 1) % kRing;
-    const unsigned long long want = cm.tag + static_cast<unsigned long long>(A.t);   // step t-1 done == t
-    if (threadIdx.x == 0) {
-        int g = 0, src = 0;
-        if (SAMPLE) {
-            wait_flag(reinterpret_cast<const unsigned long long*>(cm.peer[cm.rank] + cm.cflag_off) + ring, want, A.status);
-            g = A.cur[0];
-        } else {
-            unsigned long long best = 0ull;
-            for (int r = 0; r < cm.world; ++r) {
-                const char* sl = slot_ptr(cm, cm.rank, ring, r);
-                wait_flag(reinterpret_cast<const unsigned long long*>(sl) + 1, want, A.status);
-                const unsigned long long k = __ldcg(reinterpret_cast<const unsigned long long*>(sl));
-                if (k > best) { best = k; src = r; }
-            }
-            g = static_cast<int>(alq_maxkey_row(best));
-            if (blockIdx.x == 0) A.picks[A.t - 1] = g;
-        }
-        sh_i[0] = g;
-        sh_i[1] = src;
-    }
-    __syncthreads();
-    const int g = sh_i[0];
-    const float* pay = SAMPLE ? reinterpret_cast<const float*>(cm.peer[cm.rank] + cm.centre_off + static_cast<size_t>(ring) * cm.centre_bytes)
-                              : reinterpret_cast<const float*>(slot_ptr(cm, cm.rank, ring, sh_i[1]) + 16);
-    const float4* p4 = reinterpret_cast<const float4*>(pay);
-    for (int k = threadIdx.x; k < dv + cv; k += blockDim.x) dst[k] = __ldcg(p4 + k);
-    const float xn = __ldcg(pay + A.d + (FACTORED ? A.c : 0));
-    const float an = __ldcg(pay + A.d + (FACTORED ? A.c : 0) + 1);
-    const int local = g - cm.row_base;
-    return CentreInfo{(local >= 0 && local < cm.shard_off[cm.rank + 1] - cm.shard_off[cm.rank]) ? local : -1,
-                      FACTORED ? xn * an : xn};
-}
-
-// payload of local row `local` -> dst (a window slot, possibly on a peer); all threads of the CTA
-template <bool FACTORED>
-__device__ __forceinline__ void push_payload(const StepArgs& A, int local, float* dst) {
-    const int dv = A.d >> 2, cv = FACTORED ? (A.c >> 2) : 0;
-    const float4* x4 = reinterpret_cast<const float4*>(A.x + static_cast<int64_t>(local) * A.ldx);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int k = threadIdx.x; k < dv; k += blockDim.x) d4[k] = x4[k];
+    const int centre = SAMPLE ? A.cur[part]
+                              : static_cast<int>(alq_maxkey_row(__ldcg(&A.best[static_cast<size_t>(A.t - 1) * A.P + part])));
+    const float4* src = reinterpret_cast<const float4*>(A.x + static_cast<int64_t>(centre) * A.ldx);
+    for (int k = threadIdx.x; k < dv; k += blockDim.x) dst[k] = src[k];
     if (FACTORED) {
-        const float4* a4 = reinterpret_cast<const float4*>(A.a + static_cast<int64_t>(local) * A.lda);
-        for (int k = threadIdx.x; k < cv; k += blockDim.x) d4[dv + k] = a4[k];
+        const float4* sa = reinterpret_cast<const float4*>(A.a + static_cast<int64_t>(centre) * A.lda);
+        for (int k = threadIdx.x; k < cv; k += blockDim.x) dst[dv + k] = sa[k];
     }
-    if (threadIdx.x == 0) {
-        dst[A.d + (FACTORED ? A.c : 0)] = A.xn[local];
-        dst[A.d + (FACTORED ? A.c : 0) + 1] = FACTORED ? A.an[local] : 1.0f;
-    }
+    return CentreInfo{centre, FACTORED ? A.xn[centre] * A.an[centre] : A.xn[centre]};
 }
-
-// Multi-GPU epilogue of a step, executed by EVERY thread of EVERY CTA after the CTA's own work:
-// elects the last CTA of the grid; that CTA publishes this rank's contribution to all peers.
-//   arg-max : {local best key, the winning row's payload} into slot[t % RING][rank] of every window
-//   D^2     : (the min-distances were stored by finish_row) just the mflag[t % RING][rank] flags
-template <bool FACTORED, bool SAMPLE>
-__device__ __forceinline__ void publish_step(const StepArgs& A, int t, bool* sh_last) {
-    const CommArgs& cm = A.cm;
-    if (SAMPLE) __threadfence_system();     // this thread's remote min-distance stores are ordered before the ticket
-    else __threadfence();                   // arg-max: only the last CTA writes to peers
-    __syncthreads();
-    if (threadIdx.x == 0) *sh_last = (atomicAdd(&A.ticket[t], 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!*sh_last) return;
-    __threadfence();
-    const int ring = t % kRing;
-    const unsigned long long flag = cm.tag + static_cast<unsigned long long>(t) + 1ull;
-    if (SAMPLE) {
-        if (threadIdx.x < cm.world)
-            st_release_sys(reinterpret_cast<unsigned long long*>(cm.peer[threadIdx.x] + cm.mflag_off) + ring * cm.world + cm.rank, flag);
-        return;
-    }
-    const unsigned long long key = __ldcg(&A.best[static_cast<size_t>(t) * A.P]);
-    const int local = key ? static_cast<int>(alq_maxkey_row(key)) - cm.row_base : 0;
-    for (int g = 0; g < cm.world; ++g)
-        push_payload<FACTORED>(A, local, reinterpret_cast<float*>(slot_ptr(cm, g, ring, cm.rank) + 16));
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < cm.world) {
-        unsigned long long* sl = reinterpret_cast<unsigned long long*>(slot_ptr(cm, threadIdx.x, ring, cm.rank));
-        sl[0] = key;
-        st_release_sys(sl + 1, flag);       // release: key and payload are visible before the flag
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------
 // variant 1: direct loads
@@ -219,12 +88,10 @@ __global__ void __launch_bounds__(kV1Threads)
 step_direct_kernel(StepArgs A) {
     extern __shared__ __align__(16) float sq[];   // centre row: x part then a part
     __shared__ unsigned long long sbest[kV1Threads / 32];
-    __shared__ int sh_i[2];
-    __shared__ bool sh_last;
     const BlockSeg seg = A.segs[blockIdx.x];
     if (A.t >= A.budget[seg.part]) return;
     const int dv = A.d >> 2, cv = FACTORED ? (A.c >> 2) : 0;
-    const CentreInfo ci = load_centre<FACTORED, SAMPLE>(A, seg.part, sq, sh_i);
+    const CentreInfo ci = load_centre<FACTORED, SAMPLE>(A, seg.part, sq);
     __syncthreads();
     const int centre = ci.local;
     const float qn = ci.qn;
@@ -275,19 +142,11 @@ step_direct_kernel(StepArgs A) {
             if (b) atomicMax(&A.best[static_cast<size_t>(A.t) * A.P + seg.part], b);
         }
     }
-    if (A.cm.world > 1) publish_step<FACTORED, SAMPLE>(A, A.t, &sh_last);
 }
 
 // ------------------------------------------------------------------------------------------------
 // variant 2: bulk-copy (TMA) pipeline
 // ------------------------------------------------------------------------------------------------
-struct PipeCfg {
-    int rows_per_tile;   // R
-    int stages;
-    int tile_floats;     // R * (d + c)
-    int consumers;       // consumer warps
-};
-
 template <bool FACTORED, bool SAMPLE>
 __global__ void __launch_bounds__(32 * 17, 1)
 step_pipe_kernel(StepArgs A, PipeCfg cfg) {
@@ -300,12 +159,10 @@ step_pipe_kernel(StepArgs A, PipeCfg cfg) {
     uint64_t* empty = full + cfg.stages;
     unsigned long long* sbest = reinterpret_cast<unsigned long long*>(empty + cfg.stages);
 
-    __shared__ int sh_i[2];
-    __shared__ bool sh_last;
     const BlockSeg seg = A.segs[blockIdx.x];
     if (A.t >= A.budget[seg.part]) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const CentreInfo ci = load_centre<FACTORED, SAMPLE>(A, seg.part, sq, sh_i);
+    const CentreInfo ci = load_centre<FACTORED, SAMPLE>(A, seg.part, sq);
     const int centre = ci.local;
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg.stages; ++s) {
@@ -418,7 +275,6 @@ step_pipe_kernel(StepArgs A, PipeCfg cfg) {
             if (b) atomicMax(&A.best[static_cast<size_t>(A.t) * A.P + seg.part], b);
         }
     }
-    if (A.cm.world > 1) publish_step<FACTORED, SAMPLE>(A, A.t, &sh_last);
 }
 
 __global__ void fill_f32_kernel(float* p, int n, float v) {
@@ -429,21 +285,14 @@ __global__ void fill_f32_kernel(float* p, int n, float v) {
 // ------------------------------------------------------------------------------------------------
 // t = 0 helpers
 // ------------------------------------------------------------------------------------------------
-template <bool FACTORED>
 __global__ void __launch_bounds__(256)
 argmax_init_kernel(StepArgs A, const int* first_pick) {
     __shared__ unsigned long long sb[8];
-    __shared__ bool sh_last;
     const BlockSeg seg = A.segs[blockIdx.x];
-    if (A.cm.world == 1 && (A.budget[seg.part] <= 0 || first_pick[seg.part] >= 0)) return;
-    if (A.cm.world > 1 && threadIdx.x == 0) {
-        // peers may still be reading their windows for the previous call: wait until they are ready for this one
-        for (int r = 0; r < A.cm.world; ++r)
-            wait_flag(reinterpret_cast<const unsigned long long*>(A.cm.peer[A.cm.rank] + A.cm.ready_off) + r, A.cm.tag, A.status);
-    }
+    if (A.budget[seg.part] <= 0 || first_pick[seg.part] >= 0) return;
     unsigned long long b = 0ull;
     for (int r = seg.row_lo + threadIdx.x; r < seg.row_hi; r += blockDim.x) {
-        const unsigned long long k = alq_maxkey(A.mind[r], static_cast<uint32_t>(A.cm.row_base + r));
+        const unsigned long long k = alq_maxkey(A.mind[r], static_cast<uint32_t>(r));
         b = k > b ? k : b;
     }
     b = warp_max_u64(b);
@@ -453,34 +302,6 @@ argmax_init_kernel(StepArgs A, const int* first_pick) {
         for (int w = 1; w < 8; ++w) b = sb[w] > b ? sb[w] : b;
         if (b) atomicMax(&A.best[seg.part], b);
     }
-    if (A.cm.world > 1) publish_step<FACTORED, false>(A, 0, &sh_last);
-}
-
-// the winner of the LAST step has no following step kernel to decode it (multi-GPU arg-max)
-__global__ void comm_final_argmax_kernel(StepArgs A, int t_last) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const CommArgs& cm = A.cm;
-    unsigned long long best = 0ull;
-    for (int r = 0; r < cm.world; ++r) {
-        const char* sl = slot_ptr(cm, cm.rank, t_last % kRing, r);
-        wait_flag(reinterpret_cast<const unsigned long long*>(sl) + 1, cm.tag + static_cast<unsigned long long>(t_last) + 1ull, A.status);
-        const unsigned long long k = __ldcg(reinterpret_cast<const unsigned long long*>(sl));
-        best = k > best ? k : best;
-    }
-    A.picks[t_last] = static_cast<int>(alq_maxkey_row(best));
-}
-
-// "my window is initialised for call `tag`": one flag into every peer's ready[] array
-__global__ void comm_ready_kernel(CommArgs cm) {
-    if (blockIdx.x == 0 && threadIdx.x < cm.world) {
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned long long*>(cm.peer[threadIdx.x] + cm.ready_off) + cm.rank, cm.tag);
-    }
-}
-
-__global__ void posinv_kernel(const int* __restrict__ vpos_all, int n_global, int* __restrict__ posinv) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_global) posinv[vpos_all[g]] = g;
 }
 
 __global__ void first_pick_kernel(const int* first_pick, const int* budget, const int* pick_off, int P,
@@ -503,27 +324,13 @@ __global__ void decode_picks_kernel(const unsigned long long* best, const int* b
 // cfull[off[p] + vpos[i]] = mind[i] (labeled / padding slots stay -inf);  posinv[...] = i
 __global__ void __launch_bounds__(256)
 sample_setup_kernel(StepArgs A, int* posinv) {
-    __shared__ bool sh_last;
     const BlockSeg seg = A.segs[blockIdx.x];
-    if (A.cm.world == 1) {
-        const int off = A.cfull_off[seg.part];
-        for (int r = seg.row_lo + threadIdx.x; r < seg.row_hi; r += blockDim.x) {
-            const int k = off + A.vpos[r];
-            A.cfull[k] = A.mind[r];
-            posinv[k] = r;
-        }
-        return;
-    }
-    if (threadIdx.x == 0)
-        for (int r = 0; r < A.cm.world; ++r)
-            wait_flag(reinterpret_cast<const unsigned long long*>(A.cm.peer[A.cm.rank] + A.cm.ready_off) + r, A.cm.tag, A.status);
-    __syncthreads();
+    const int off = A.cfull_off[seg.part];
     for (int r = seg.row_lo + threadIdx.x; r < seg.row_hi; r += blockDim.x) {
-        const int vp = A.vpos[r];
-        const float m = A.mind[r];
-        for (int g = 0; g < A.cm.world; ++g) reinterpret_cast<float*>(A.cm.peer[g] + A.cm.mfull_off[0])[vp] = m;
+        const int k = off + A.vpos[r];
+        A.cfull[k] = A.mind[r];
+        posinv[k] = r;
     }
-    publish_step<false, true>(A, 0, &sh_last);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -557,56 +364,12 @@ struct SampleArgs {
     int* picks;
     int* status;                 // sticky error flag
     int t;
-    StepArgs step;               // rows / comm description (multi-GPU: owner pushes the centre payload)
-    int factored;
     long long* dbg;              // optional phase timestamps (ALQ_SAMPLE_DEBUG=1), 8 per launch
 };
 
 constexpr int kSampThreads = 1024;
 constexpr int kCL = 8;             // CTAs per cluster == per partition (portable cluster size)
 
-
-// NumPy pairwise_sum leaf (n <= 128) evaluated by an 8-lane group, bit-exact:
-//   r[j] = a[j]; r[j] += a[i+j] for i = 8,16,..; ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); then the
-//   n % 8 tail added one by one.
-__device__ __forceinline__ float leaf_sum_group(const float* a, int len, int g_lane, unsigned gmask) {
-    float res;
-    if (len < 8) {
-        res = 0.f;
-        if (g_lane == 0)
-            for (int i = 0; i < len; ++i) res += fmaxf(a[i], 0.f);
-        return res;
-    }
-    const int stop = len - (len & 7);
-    // issue every load of this lane first (<= 16: a leaf has <= 128 entries), then add in NumPy's order
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (8 * j + g_lane < stop) ? __ldcg(a + 8 * j + g_lane) : 0.f;
-    float tail[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) tail[j] = (g_lane == 0 && stop + j < len) ? __ldcg(a + stop + j) : 0.f;
-    float r = fmaxf(v[0], 0.f);                      // prob = clip(min_dist, 0) (coreset_sampler.py:84)
-#pragma unroll
-    for (int j = 1; j < 16; ++j)
-        if (8 * j < stop) r += fmaxf(v[j], 0.f);
-    r = r + __shfl_down_sync(gmask, r, 1, 8);   // lanes 0,2,4,6: r0+r1, r2+r3, ...
-    r = r + __shfl_down_sync(gmask, r, 2, 8);   // lanes 0,4
-    r = r + __shfl_down_sync(gmask, r, 4, 8);   // lane 0
-    res = r;
-    if (g_lane == 0) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-            if (stop + j < len) res += fmaxf(tail[j], 0.f);
-    }
-    return res;
-}
-
-// prob = c / S in IEEE fp32 (what NumPy computes).  Zero numerators (every labeled / picked slot) would take
-// the division's special-operand slow path: 0 / S == +0 for S > 0, so answer those without dividing.
-__device__ __forceinline__ double prob64(float raw, float total32) {
-    const float c = fmaxf(raw, 0.f);
-    return c > 0.f ? static_cast<double>(__fdiv_rn(c, total32)) : 0.0;
-}
 
 // One thread-block CLUSTER (kCL CTAs on kCL SMs) per partition.  The three dependent stages of a
 // D^2 draw -- np.sum(prob) -> prob = c / S -> inverse-CDF search -- are separated by two cluster
@@ -632,17 +395,9 @@ sample_cluster_kernel(SampleArgs A) {
     const int t = A.t;
     if (t >= S.budget) return;                     // uniform over the cluster
     if (t == 0 && A.first_pick[p] >= 0) return;    // chosen by the caller (nothing labeled yet)
-    const CommArgs& cm = A.step.cm;
-    float* cf = cm.world > 1 ? reinterpret_cast<float*>(cm.peer[cm.rank] + cm.mfull_off[t & 1]) : A.cfull + S.cfull_off;
+    float* cf = A.cfull + S.cfull_off;
     const int n = S.full_n, K = S.n_leaves;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (cm.world > 1) {     // every rank's min-distances of step t must have landed in the local replica
-        if (threadIdx.x == 0)
-            for (int r = 0; r < cm.world; ++r)
-                wait_flag(reinterpret_cast<const unsigned long long*>(cm.peer[cm.rank] + cm.mflag_off) + (t % kRing) * cm.world + r,
-                          cm.tag + static_cast<unsigned long long>(t) + 1ull, A.status);
-        __syncthreads();
-    }
     const int* leaf_off = A.leaf_off + S.leaf_base;
     float* leafval = A.leafval + S.leaf_base;
     // The combine schedule (3 ints per internal node) is needed only after the leaf sums: start copying it
@@ -821,25 +576,6 @@ sample_cluster_kernel(SampleArgs A) {
         A.picks[S.pick_off + t] = row;
         sh_hit = row;
     }
-    if (cm.world > 1) {
-        // the rank that owns the drawn row pushes it (x, a, norms) into every window as the next centre
-        __syncthreads();
-        const int row = sh_hit;
-        const int local = row - cm.row_base;
-        if (local >= 0 && local < cm.shard_off[cm.rank + 1] - cm.shard_off[cm.rank]) {
-            const int ring = t % kRing;
-            for (int g = 0; g < cm.world; ++g) {
-                float* dst = reinterpret_cast<float*>(cm.peer[g] + cm.centre_off + static_cast<size_t>(ring) * cm.centre_bytes);
-                if (A.factored) push_payload<true>(A.step, local, dst);
-                else push_payload<false>(A.step, local, dst);
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x < cm.world)
-                st_release_sys(reinterpret_cast<unsigned long long*>(cm.peer[threadIdx.x] + cm.cflag_off) + ring,
-                               cm.tag + static_cast<unsigned long long>(t) + 1ull);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -870,27 +606,6 @@ struct TreeBuilder {
     }
     std::vector<std::pair<int, int>> internal_refs;
 };
-
-void build_segments(int P, const int32_t* part_off, const int32_t* budget, int target_blocks,
-                    std::vector<BlockSeg>& segs) {
-    int64_t total = 0;
-    for (int p = 0; p < P; ++p)
-        if (budget[p] > 0) total += part_off[p + 1] - part_off[p];
-    for (int p = 0; p < P; ++p) {
-        const int rows = part_off[p + 1] - part_off[p];
-        if (rows <= 0 || budget[p] <= 0) continue;
-        int nb = static_cast<int>((static_cast<int64_t>(target_blocks) * rows + total / 2) / std::max<int64_t>(total, 1));
-        nb = std::max(1, std::min(nb, rows));
-        for (int b = 0; b < nb; ++b) {
-            BlockSeg s;
-            s.row_lo = part_off[p] + static_cast<int>(static_cast<int64_t>(rows) * b / nb);
-            s.row_hi = part_off[p] + static_cast<int>(static_cast<int64_t>(rows) * (b + 1) / nb);
-            s.part = p;
-            s.pad = 0;
-            if (s.row_hi > s.row_lo) segs.push_back(s);
-        }
-    }
-}
 
 template <bool FACTORED, bool SAMPLE>
 void launch_step(int variant, int grid, cudaStream_t st, const StepArgs& A, const PipeCfg& cfg, size_t smem_v1,
@@ -934,30 +649,28 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: D^2 sampling needs vpos and full_n");
     if (D->part_off_host[0] != 0 || D->part_off_host[P] != n)
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: part_off must span [0, n]");
-    // ---- multi-GPU group? ---------------------------------------------------------------------------
+    // ---- multi-GPU group? (every array is global and replicated; rank r streams its shard: include/alq.h) ----
     const bool comm = D->shard_off_host != nullptr && ctx->comm.world > 1;
     const AlqComm& G = ctx->comm;
-    int64_t n_global = n;
     if (D->shard_off_host && ctx->comm.world <= 1 && D->shard_off_host[1] != n)
         ALQ_FAIL(ctx, ALQ_ERR_STATE, "alq_greedy_select: shard_off given but no multi-GPU group (alq_comm_create/connect)");
     if (comm) {
         if (!G.connected) ALQ_FAIL(ctx, ALQ_ERR_STATE, "alq_greedy_select: alq_comm_connect has not been called");
         if (P != 1) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: the multi-GPU loop is for one global partition");
-        if (D->first_pick_host && D->first_pick_host[0] >= 0)
-            ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: first_pick is not supported in multi-GPU mode");
-        if (D->shard_off_host[0] != 0 || D->shard_off_host[G.rank + 1] - D->shard_off_host[G.rank] != n)
-            ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: shard_off does not match this rank's n");
-        n_global = D->shard_off_host[G.world];
-        if (sample && !D->vpos_all) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: vpos_all is required for multi-GPU D^2 sampling");
+        if (D->shard_off_host[0] != 0 || D->shard_off_host[G.world] != n)
+            ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: shard_off must span the n global candidate rows");
+        for (int r = 0; r < G.world; ++r)
+            if (D->shard_off_host[r + 1] < D->shard_off_host[r])
+                ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: shard_off must be non-decreasing");
     }
     std::vector<int> pick_off(P + 1, 0), first_pick(P, -1);
     int bmax = 0;
     for (int p = 0; p < P; ++p) {
         const int rows = D->part_off_host[p + 1] - D->part_off_host[p];
         const int b = D->budget_host[p];
-        if (rows < 0 || b < 0 || b > (comm ? n_global : rows))
+        if (rows < 0 || b < 0 || b > rows)
             ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: partition %d has %d rows but budget %d", p, rows, b);
-        if (sample && (D->full_n_host[p] < (comm ? n_global : rows) || D->full_n_host[p] > (2 << 20)))
+        if (sample && (D->full_n_host[p] < rows || D->full_n_host[p] > (2 << 20)))
             ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: full_n[%d]=%d out of range", p, D->full_n_host[p]);
         pick_off[p + 1] = pick_off[p] + b;
         bmax = std::max(bmax, b);
@@ -978,6 +691,20 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     PipeCfg cfg{};
     size_t smem_v2 = 0;
     int variant = D->variant ? D->variant : ctx->greedy_variant;
+    if (variant == 0) {
+        const char* env = getenv("ALQ_GREEDY_VARIANT");   // debugging aid: force a variant
+        if (env && env[0] >= '1' && env[0] <= '3' && env[1] == 0) variant = env[0] - '0';
+    }
+    if (variant == 0 || variant == 3 || comm) {
+        // the whole loop as one persistent cooperative launch (alq_greedy_persist.cu)
+        const int rc3 = alq_greedy_persist(ctx, D, stream);
+        if (rc3 != kPersistNotApplicable) return rc3;
+        if (variant == 3 || comm)
+            ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: the persistent loop does not fit this problem "
+                                           "(more active partitions than SMs, a partition beyond %d tree leaves, or a row too large for the ring)%s",
+                     4096, comm ? "; the multi-GPU loop has no other variant" : "");
+        variant = 0;
+    }
     {
         const size_t row_bytes = static_cast<size_t>(d + c) * 4;
         const size_t centre_bytes = static_cast<size_t>((d + c + 31) & ~31) * 4;
@@ -997,11 +724,6 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         cfg.consumers = std::max(1, std::min(16, stages));
         smem_v2 = centre_bytes + stages * tile_bytes + 2 * stages * sizeof(uint64_t) + 16 * sizeof(unsigned long long) + 64;
         const bool v2_ok = stages >= 3 && (row_bytes % 16 == 0) && (static_cast<size_t>(d) * 4 % 16 == 0);
-        if (variant == 0) {
-            const char* env = getenv("ALQ_GREEDY_VARIANT");   // debugging aid: force a variant
-            if (env && (env[0] == '1' || env[0] == '2') && env[1] == 0) variant = env[0] - '0';
-            if (variant == 2 && !v2_ok) variant = 1;
-        }
         if (variant == 0) variant = v2_ok ? 2 : 1;
         if (variant == 2 && !v2_ok) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: variant 2 does not fit (row too large)");
         if (variant != 1 && variant != 2) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_greedy_select: unknown variant");
@@ -1067,7 +789,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
                                       level_off_all.size() * 4 + 4, comb_all.size() * 4 + 4,
                                       static_cast<size_t>(cfull_total) * 4 + 16, static_cast<size_t>(cfull_total) * 4 + 16,
                                       leaf_off_all.size() * 4 + 4,
-                                      static_cast<size_t>(P) * kCL * 8, static_cast<size_t>(bmax + 2) * 4, 64});
+                                      static_cast<size_t>(P) * kCL * 8, 64});
     int rc = alq_scratch_reserve(ctx, need);
     if (rc) return rc;
     ScratchCursor cur(ctx->scratch);
@@ -1088,33 +810,6 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     float* d_leafval = cur.take<float>(leaf_off_all.size() + 1);
     double* d_cta_part = cur.take<double>(static_cast<size_t>(P) * kCL);
     int* d_status = cur.take<int>(1);
-    unsigned int* d_ticket = cur.take<unsigned int>(bmax + 2);
-
-    // ---- multi-GPU window layout (identical on every rank) and per-call epoch tag ------------------------
-    CommArgs cm{};
-    cm.world = 1;
-    if (comm) {
-        cm.world = G.world; cm.rank = G.rank; cm.row_base = D->shard_off_host[G.rank]; cm.n_global = static_cast<int>(n_global);
-        for (int r = 0; r <= G.world; ++r) cm.shard_off[r] = D->shard_off_host[r];
-        for (int r = 0; r < G.world; ++r) cm.peer[r] = G.peer[r];
-        cm.payload_floats = (d + c + 2 + 3) & ~3;
-        auto up = [](size_t v) { return (v + 127) & ~size_t(127); };
-        size_t off = 0;
-        cm.ready_off = off; off = up(off + 8 * G.world);
-        cm.slot_bytes = up(16 + static_cast<size_t>(cm.payload_floats) * 4);
-        cm.slot_off = off; off = up(off + cm.slot_bytes * kRing * G.world);
-        cm.mflag_off = off; off = up(off + 8 * kRing * G.world);
-        cm.cflag_off = off; off = up(off + 8 * kRing);
-        cm.centre_bytes = up(static_cast<size_t>(cm.payload_floats) * 4);
-        cm.centre_off = off; off = up(off + cm.centre_bytes * kRing);
-        const size_t mf = up((static_cast<size_t>(sample ? D->full_n_host[0] : 0) + 4) * 4);
-        cm.mfull_off[0] = off; off += mf;
-        cm.mfull_off[1] = off; off += mf;
-        if (off > G.greedy_bytes())
-            ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_greedy_select: peer window too small (%zu needed, %zu usable)", off, G.greedy_bytes());
-        ctx->comm.epoch += 1;
-        cm.tag = ctx->comm.epoch << 32;
-    }
 
     // pageable sources: the runtime stages them before returning, so the vectors may die afterwards
     ALQ_CUDA(ctx, cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(BlockSeg), cudaMemcpyHostToDevice, st));
@@ -1123,7 +818,6 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     ALQ_CUDA(ctx, cudaMemcpyAsync(d_first, first_pick.data(), P * sizeof(int), cudaMemcpyHostToDevice, st));
     ALQ_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(int), st));
     ALQ_CUDA(ctx, cudaMemsetAsync(d_cur, 0, P * sizeof(int), st));
-    ALQ_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, static_cast<size_t>(bmax + 2) * 4, st));
     if (sample) {
         ALQ_CUDA(ctx, cudaMemcpyAsync(d_cfull_off, cfull_off.data(), P * sizeof(int), cudaMemcpyHostToDevice, st));
         ALQ_CUDA(ctx, cudaMemcpyAsync(d_unif, D->uniforms_host, total_picks * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1134,13 +828,6 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
             ALQ_CUDA(ctx, cudaMemcpyAsync(d_comb, comb_all.data(), comb_all.size() * 4, cudaMemcpyHostToDevice, st));
         fill_f32_kernel<<<(cfull_total + 4 + 255) / 256, 256, 0, st>>>(d_cfull, cfull_total + 4, -INFINITY);
         ALQ_LAUNCH_CHECK(ctx);
-        if (comm) {   // both replicas of the running min-distances start at -inf (labeled and padding slots stay there)
-            for (int b2 = 0; b2 < 2; ++b2) {
-                fill_f32_kernel<<<(cfull_total + 4 + 255) / 256, 256, 0, st>>>(
-                    reinterpret_cast<float*>(G.window + cm.mfull_off[b2]), cfull_total + 4, -INFINITY);
-                ALQ_LAUNCH_CHECK(ctx);
-            }
-        }
         ALQ_CUDA(ctx, cudaMemsetAsync(d_posinv, 0xff, static_cast<size_t>(cfull_total + 4) * 4, st));
     } else {
         ALQ_CUDA(ctx, cudaMemsetAsync(d_best, 0, n_best * 8, st));
@@ -1154,7 +841,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     A.segs = d_segs; A.budget = d_budget; A.P = P;
     A.best = d_best; A.cur = d_cur;
     A.vpos = D->vpos; A.cfull = d_cfull; A.cfull_off = d_cfull_off;
-    A.cm = cm; A.ticket = d_ticket; A.status = d_status; A.picks = D->picks;
+    A.status = d_status; A.picks = D->picks;
 
     cudaError_t ae = cudaSuccess;
     if (factored) ae = sample ? set_step_attrs<true, true>(smem_v1, variant == 2 ? smem_v2 : 0)
@@ -1169,7 +856,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         SA.sched = d_sched; SA.leaf_off = d_leaf_off; SA.level_off = d_level_off; SA.comb = d_comb;
         SA.cfull = d_cfull; SA.posinv = d_posinv;
         SA.leafval = d_leafval; SA.cta_part = d_cta_part; SA.uniforms = d_unif; SA.first_pick = d_first; SA.cur = d_cur;
-        SA.picks = D->picks; SA.status = d_status; SA.step = A; SA.factored = factored ? 1 : 0;
+        SA.picks = D->picks; SA.status = d_status;
         if (getenv("ALQ_SAMPLE_DEBUG")) {
             static long long* dbg_buf = nullptr;
             if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * 8 * sizeof(long long));
@@ -1187,28 +874,18 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
     }
 
     // ---- t = 0 ------------------------------------------------------------------------------------------
-    if (comm) {
-        comm_ready_kernel<<<1, 32, 0, st>>>(cm);     // after the fills above, in stream order
-        ALQ_LAUNCH_CHECK(ctx);
-    }
     first_pick_kernel<<<(P + 127) / 128, 128, 0, st>>>(d_first, d_budget, d_pick_off, P, sample ? nullptr : d_best,
                                                        d_cur, D->picks);
     ALQ_LAUNCH_CHECK(ctx);
     A.t = 0;
     if (sample) {
-        if (comm) {
-            posinv_kernel<<<static_cast<int>((n_global + 255) / 256), 256, 0, st>>>(D->vpos_all, static_cast<int>(n_global), d_posinv);
-            ALQ_LAUNCH_CHECK(ctx);
-        }
         sample_setup_kernel<<<grid, 256, 0, st>>>(A, d_posinv);
         ALQ_LAUNCH_CHECK(ctx);
         SA.t = 0;
-        SA.step = A;
         sample_cluster_kernel<<<P * kCL, kSampThreads, samp_smem, st>>>(SA);
         ALQ_LAUNCH_CHECK(ctx);
     } else {
-        if (factored) argmax_init_kernel<true><<<grid, 256, 0, st>>>(A, d_first);
-        else argmax_init_kernel<false><<<grid, 256, 0, st>>>(A, d_first);
+        argmax_init_kernel<<<grid, 256, 0, st>>>(A, d_first);
         ALQ_LAUNCH_CHECK(ctx);
     }
 
@@ -1239,21 +916,16 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         if (timed) cudaEventRecord(evs.back(), st);
         if (sample) {
             SA.t = t;
-            SA.step = A;
             sample_cluster_kernel<<<P * kCL, kSampThreads, samp_smem, st>>>(SA);
             ALQ_LAUNCH_CHECK(ctx);
         }
     }
-    if (!sample && !comm) {
+    if (!sample) {
         decode_picks_kernel<<<(P * bmax + 255) / 256, 256, 0, st>>>(d_best, d_budget, d_pick_off, P, bmax, D->picks);
         ALQ_LAUNCH_CHECK(ctx);
     }
-    if (!sample && comm) {
-        comm_final_argmax_kernel<<<1, 32, 0, st>>>(A, bmax - 1);
-        ALQ_LAUNCH_CHECK(ctx);
-    }
     int status = 0;
-    if (timing || sample || comm) {
+    if (timing || sample) {
         // the sampling variant reports a sticky numeric status; timing needs the events resolved
         ALQ_CUDA(ctx, cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
         ALQ_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1275,10 +947,12 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, evs[i], evs[i + 1]) == cudaSuccess) { acc += ms; ++cnt; }
         }
-        *D->step_kernel_ms_host = cnt ? static_cast<float>(acc / cnt) : 0.f;
+        D->step_kernel_ms_host[0] = cnt ? static_cast<float>(acc / cnt) : 0.f;
+        D->step_kernel_ms_host[1] = 0.f;
+        D->step_kernel_ms_host[2] = static_cast<float>(cnt);
+        D->step_kernel_ms_host[3] = static_cast<float>(variant);
     }
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
-    if (status == ALQ_ERR_STATE) ALQ_FAIL(ctx, status, "alq_greedy_select: timed out waiting for a peer GPU's step flag");
     if (status != 0) ALQ_FAIL(ctx, status, "alq_greedy_select: non-finite or empty probability mass during D^2 sampling");
     return ALQ_OK;
 }

@@ -90,7 +90,7 @@ class Engine:
         return self
 
     def set_option(self, key: str, value: int):
-        """'k3_impl': 0 auto / 1 fp32 SIMT / 2 tcgen05 3xTF32;  'greedy_variant': 0 auto / 1 direct / 2 pipeline;
+        """'k3_impl': 0 auto / 1 fp32 SIMT / 2 tcgen05 3xTF32;  'greedy_variant': 0 auto / 1 direct / 2 pipeline / 3 persistent;  'spin_timeout_ms';
         'select_impl': 0 auto / 1 multi-kernel / 2 cluster;  'base_impl': 0 auto / 1 sequential / 2 parallel lists."""
         self._check(self.lib.alq_set_option(self._h, key.encode(), int(value)), "alq_set_option")
 
@@ -267,6 +267,15 @@ class Engine:
         return out
 
     # -- K4 / K5 ---------------------------------------------------------------------------------------
+    def leaf_bounds(self, n: int) -> np.ndarray:
+        """Leaf boundaries of NumPy's float32 pairwise summation over n entries (host helper of the library)."""
+        cap = int(n) // 64 + 8
+        out = np.empty(cap, dtype=np.int32)
+        k = int(self.lib.alq_pairwise_leaf_bounds(int(n), C.c_void_p(out.ctypes.data), cap))
+        if k < 0:
+            raise AlqError(f"alq_pairwise_leaf_bounds({n}) failed")
+        return out[:k + 1].copy()
+
     def greedy_select(self, x: torch.Tensor, xn: torch.Tensor, mind: torch.Tensor,
                       part_off: Sequence[int], budget: Sequence[int],
                       a: Optional[torch.Tensor] = None, an: Optional[torch.Tensor] = None,
@@ -274,9 +283,14 @@ class Engine:
                       full_n: Optional[Sequence[int]] = None,
                       first_pick: Optional[Sequence[int]] = None, variant: int = 0,
                       time_steps: bool = False, shard_off: Optional[Sequence[int]] = None,
-                      vpos_all: Optional[torch.Tensor] = None):
+                      shard_pos: Optional[Sequence[int]] = None):
         """Runs the whole selection loop on the device; returns the picked row ids (host int32,
-        partition-major, pick order) and, with time_steps, the mean streaming-kernel time in ms."""
+        partition-major, pick order) and, with time_steps, the mean time of a step's streaming phase in ms
+        (the full record -- streaming, selection, steps, variant -- is kept in `self.last_greedy_timing`).
+
+        Multi-GPU (comm_init): every tensor is the GLOBAL, replicated array; `shard_off` [world + 1] says which
+        rows each rank streams and, for D^2 sampling, `shard_pos` [world + 1] the matching leaf-aligned position
+        ranges of the full array (sharding.plan_shards)."""
         x = _f32c(x, "x")
         n, d = x.shape
         part_off_h = np.ascontiguousarray(part_off, dtype=np.int32)
@@ -309,7 +323,7 @@ class Engine:
             desc.uniforms_host = u.ctypes.data
             desc.vpos = vpos.data_ptr()
             desc.full_n_host = full_h.ctypes.data
-            keep += [u, full_h]
+            keep += [u, full_h, vpos]
         if first_pick is not None:
             fp = np.ascontiguousarray(first_pick, dtype=np.int32)
             desc.first_pick_host = fp.ctypes.data
@@ -318,15 +332,20 @@ class Engine:
             so = np.ascontiguousarray(shard_off, dtype=np.int32)
             desc.shard_off_host = so.ctypes.data
             keep.append(so)
-            if vpos_all is not None:
-                desc.vpos_all = vpos_all.data_ptr()
-                keep.append(vpos_all)
+            if shard_pos is not None:
+                sp = np.ascontiguousarray(shard_pos, dtype=np.int32)
+                desc.shard_pos_host = sp.ctypes.data
+                keep.append(sp)
         desc.picks = picks.data_ptr()
         desc.variant = int(variant)
-        ms = C.c_float(0.0)
+        ms = (C.c_float * 4)()
         if time_steps:
             desc.step_kernel_ms_host = C.addressof(ms)
         self._check(self.lib.alq_greedy_select(self._h, C.byref(desc), self._stream()), "alq_greedy_select")
         out = picks[:total].cpu().numpy()
         del keep
-        return (out, float(ms.value)) if time_steps else out
+        if time_steps:
+            self.last_greedy_timing = {"stream_ms": float(ms[0]), "select_ms": float(ms[1]), "steps": int(ms[2]),
+                                       "variant": int(ms[3])}
+            return out, float(ms[0])
+        return out

@@ -140,10 +140,7 @@ class CoresetQuery(EngineMixin):
         union = np.asarray(self.get_idxs_for_coreset(), dtype=np.int64)      # RNG: two permutations (:22-23)
         group = getattr(self, "_shard_group", None)
         if group is not None and group.world_size > 1:
-            is_lab = self.already_labeled_idxs(boolean=True)[union]
-            shares = [int((~is_lab[a:b]).sum()) for a, b in (group.row_range(len(union), q) for q in range(group.world_size))]
-            if min(shares) > 0:                  # every rank owns candidates: shard; else every rank runs the whole query
-                return self._query_global_sharded(union, budget, group)
+            return self._query_global_sharded(union, budget, group)
         cacheable = (self.freeze_feature and not self.GRADIENT_EMBEDDING
                      and self.subset_unlabeled is None and self.subset_labeled is None)
         saved = getattr(self, "_saved_embeddings", None)
@@ -163,12 +160,14 @@ class CoresetQuery(EngineMixin):
         labeled_idxs_cur_rd = union[cand_pos[picks]].tolist()
         return labeled_idxs_cur_rd, len(labeled_idxs_cur_rd)
 
-    # ---- the same query with the rows of the union sharded over the ranks of a ShardGroup -------------
+    # ---- the same query with the work sharded over the ranks of a ShardGroup ------------------------------
     def _query_global_sharded(self, union, budget, group):
-        """Every rank forwards rows [lo, hi) of the sorted union, keeps its unlabeled rows as candidates,
-        receives the (few) labeled rows of the other ranks, and the selection loop exchanges its per-step
-        winner through the engine's peer-memory windows.  Host bookkeeping and the RNG stream are replicated,
-        so every rank returns the same list as the single-GPU query."""
+        """Every rank forwards rows [lo, hi) of the sorted union; the embeddings (and BADGE factors) are
+        all-gathered once, so every rank holds a replica of every row (a few hundred MB next to 180 GB).  The
+        distance pass (K3) and the selection loop (K4 / K5) are then sharded by candidate row: a new centre is
+        announced as a row id through the engine's peer-memory windows and read from the local replica.  Host
+        bookkeeping and the RNG stream are replicated, so every rank returns the single-GPU list."""
+        from ..sharding import plan_shards
         eng = self.get_engine()
         is_lab = self.already_labeled_idxs(boolean=True)[union]
         budget = int(min(self.available_query_idxs(boolean=True)[union].sum(), budget))
@@ -189,54 +188,40 @@ class CoresetQuery(EngineMixin):
             _, emb = self._forward_pool(union[lo:hi].tolist(), self.feature_net, want_features=True)
             factors = None
         dev = emb.device
-        my_lab = lab_pos[(lab_pos >= lo) & (lab_pos < hi)] - lo
-        my_cand = cand_pos[(cand_pos >= lo) & (cand_pos < hi)] - lo
-        lab_counts = [int(((lab_pos >= a) & (lab_pos < b)).sum()) for a, b in bounds]
-        cand_counts = [int(((cand_pos >= a) & (cand_pos < b)).sum()) for a, b in bounds]
-        shard_off = np.concatenate(([0], np.cumsum(cand_counts))).astype(np.int32)
-        X, XA = _gather(emb, my_cand, dev), _gather(factors, my_cand, dev)
+        counts = [b - a for a, b in bounds]
+        feats = group.all_gather_rows(emb, counts)                                 # [n_u, D] on every rank
+        factors = group.all_gather_rows(factors, counts) if factors is not None else None
+        X, XA = _gather(feats, cand_pos, dev), _gather(factors, cand_pos, dev)
         xn = eng.row_norm2(X)
         xan = eng.row_norm2(XA) if XA is not None else None
+        shard_off, shard_pos = plan_shards(cand_pos, n_u, G, leaf_aligned=self.RANDOMIZE)
+        s0, s1 = int(shard_off[r]), int(shard_off[r + 1])
+
+        def sl(t):
+            return t[s0:s1] if t is not None else None
+
         mind = torch.full((X.shape[0],), float("inf"), dtype=torch.float32, device=dev)
-        head = []
+        first_pick = -1
         if len(lab_pos):
-            Y = group.all_gather_rows(_gather(emb, my_lab, dev), lab_counts)
-            YA = group.all_gather_rows(_gather(factors, my_lab, dev), lab_counts) if factors is not None else None
+            Y, YA = _gather(feats, lab_pos, dev), _gather(factors, lab_pos, dev)
+            if s1 > s0:
+                eng.min_dist(X[s0:s1], xn[s0:s1], Y, eng.row_norm2(Y), sl(XA), sl(xan), YA,
+                             eng.row_norm2(YA) if YA is not None else None, out=mind[s0:s1])
+        elif self.RANDOMIZE:
+            first_pick = int(first[0])            # nothing labeled: position == candidate row (coreset_sampler.py:98)
         else:
-            # nothing labeled: first centre by np.random.choice (D^2) / minimax (arg-max), then it plays the
-            # role of the labeled set for the remaining budget - 1 picks (coreset_sampler.py:97-100)
-            allX = group.all_gather_rows(X, cand_counts)
-            allA = group.all_gather_rows(XA, cand_counts) if XA is not None else None
-            if self.RANDOMIZE:
-                q0 = int(first[0])
-            else:
-                alln = eng.row_norm2(allX)
-                alla = eng.row_norm2(allA) if allA is not None else None
-                far = eng.min_dist(X, xn, allX, alln, XA, xan, allA, alla, reduce_max=True)
-                far_all = group.all_gather_rows(far, cand_counts)
-                q0 = eng.argmin(far_all)
-            head = [q0]
-            Y = allX[q0:q0 + 1].contiguous()
-            YA = allA[q0:q0 + 1].contiguous() if allA is not None else None
-            if shard_off[r] <= q0 < shard_off[r + 1]:
-                pass        # excluded below, after the distance pass
-            budget -= 1
-            unif = [unif[0][1:]]
-        if Y.shape[0]:
-            eng.min_dist(X, xn, Y, eng.row_norm2(Y), XA, xan, YA, eng.row_norm2(YA) if YA is not None else None,
-                         out=mind)
-        if head and shard_off[r] <= head[0] < shard_off[r + 1]:
-            mind[head[0] - int(shard_off[r])] = float("-inf")     # the first centre is not a candidate any more
-        picks = []
-        if budget > 0:
-            vpos_all = torch.as_tensor(cand_pos.astype(np.int32), device=dev)
-            picks = eng.greedy_select(
-                X, xn, mind, [0, X.shape[0]], [budget], a=XA, an=xan,
-                uniforms=unif[0] if self.RANDOMIZE else None,
-                vpos=vpos_all[int(shard_off[r]):int(shard_off[r + 1])].contiguous() if self.RANDOMIZE else None,
-                full_n=[n_u] if self.RANDOMIZE else None, shard_off=shard_off, vpos_all=vpos_all).tolist()
-        chosen = head + picks
-        labeled_idxs_cur_rd = union[cand_pos[np.asarray(chosen, dtype=np.int64)]].tolist()
+            far = torch.empty(0, dtype=torch.float32, device=dev)
+            if s1 > s0:
+                far = eng.min_dist(X[s0:s1], xn[s0:s1], X, xn, sl(XA), sl(xan), XA, xan, reduce_max=True)
+            far_all = group.all_gather_rows(far, [int(shard_off[q + 1] - shard_off[q]) for q in range(G)])
+            first_pick = eng.argmin(far_all)      # minimax centre, coreset_sampler.py:100
+        picks = eng.greedy_select(
+            X, xn, mind, [0, X.shape[0]], [budget], a=XA, an=xan,
+            uniforms=unif[0] if self.RANDOMIZE else None,
+            vpos=torch.as_tensor(cand_pos.astype(np.int32), device=dev) if self.RANDOMIZE else None,
+            full_n=[n_u] if self.RANDOMIZE else None, first_pick=[first_pick],
+            shard_off=shard_off, shard_pos=shard_pos)
+        labeled_idxs_cur_rd = union[cand_pos[np.asarray(picks, dtype=np.int64)]].tolist()
         return labeled_idxs_cur_rd, len(labeled_idxs_cur_rd)
 
 

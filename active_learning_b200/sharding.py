@@ -15,6 +15,50 @@ import torch
 import torch.distributed as dist
 
 
+def pairwise_leaf_bounds(n: int) -> np.ndarray:
+    """Leaf boundaries of NumPy's float32 pairwise summation over n entries (blocks of <= 128, splits at n/2 rounded
+    down to a multiple of 8) -- the host twin of the library's alq_pairwise_leaf_bounds (tests pin them together)."""
+    out = []
+
+    def rec(lo, m):
+        if m <= 128:
+            out.append(lo)
+            return
+        half = m // 2
+        half -= half % 8
+        rec(lo, half)
+        rec(lo + half, m - half)
+
+    rec(0, int(n))
+    out.append(int(n))
+    return np.asarray(out, dtype=np.int32)
+
+
+def plan_shards(cand_pos: np.ndarray, full_n: int, world: int, leaf_aligned: bool, leaf_bounds=None):
+    """Split the (sorted) candidate rows of one global partition over `world` ranks.
+
+    Returns (shard_off [world + 1] row offsets, shard_pos [world + 1] position offsets or None).  For the arg-max loop
+    any split works: equal row counts.  For D^2 sampling every rank must own whole leaves of NumPy's pairwise-sum tree
+    over the full (labeled + unlabeled) array, so the cuts are moved to the nearest leaf boundary."""
+    n = len(cand_pos)
+    if not leaf_aligned:
+        return np.asarray([r * n // world for r in range(world + 1)], dtype=np.int32), None
+    bounds = pairwise_leaf_bounds(full_n) if leaf_bounds is None else np.asarray(leaf_bounds)
+    shard_pos = [0]
+    for r in range(1, world):
+        target = int(cand_pos[min(n - 1, r * n // world)]) if n else 0
+        k = int(np.searchsorted(bounds, target))
+        k = min(max(k, 0), len(bounds) - 1)
+        if k > 0 and target - bounds[k - 1] < bounds[k] - target:
+            k -= 1
+        shard_pos.append(max(int(bounds[k]), shard_pos[-1]))
+    shard_pos.append(int(full_n))
+    shard_pos = np.asarray(shard_pos, dtype=np.int32)
+    shard_off = np.searchsorted(np.asarray(cand_pos), shard_pos, side="left").astype(np.int32)
+    shard_off[0], shard_off[-1] = 0, n
+    return shard_off, shard_pos
+
+
 class ShardGroup:
     def __init__(self, process_group=None):
         if not dist.is_initialized():

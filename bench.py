@@ -270,90 +270,136 @@ def workload_config(gpus):
 # ----------------------------------------------------------------------------------------------
 # extra workloads (N = 1): CoreSet and BADGE tails at the north-star shapes
 # ----------------------------------------------------------------------------------------------
-def run_greedy_workload(eng, kind, peak, steps, warmup, world=1, rank=0):
-    """CoreSet / BADGE tail at the north-star shape.  world > 1: STRONG scaling -- the same 80 000
-    candidates are row-sharded over the ranks, the labeled set is replicated, and the per-step winner is
-    exchanged through peer-memory windows from inside the step kernels (no NCCL call in the loop)."""
+def run_greedy_workload(eng, kind, peak, steps, warmup, world=1, rank=0, check_picks=400):
+    """CoreSet / BADGE tail at the north-star shape.  world > 1: STRONG scaling -- the same 80 000 candidates; every
+    rank holds a replica of the rows (the engine's multi-GPU contract: a centre is announced as a row id), the distance
+    pass (K3) and the selection loop (K4 / K5) are sharded by candidate row, and the per-step agreement on the centre
+    runs inside ONE persistent kernel per rank over peer-memory windows (no NCCL call and no launch in the loop).
+    The first `check_picks` picks are compared with a single-GPU run of the same loop on the same data."""
     import torch.distributed as dist
+    from active_learning_b200.sharding import plan_shards
     dev = eng.device
-    lo, hi = rank * N_ROWS // world, (rank + 1) * N_ROWS // world
-    shard_off = [r * N_ROWS // world for r in range(world + 1)] if world > 1 else None
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    X = torch.relu(torch.randn(hi - lo, EMB_DIM, device=dev, generator=g))
-    gy = torch.Generator(device=dev).manual_seed(1)            # labeled rows: identical on every rank
-    Y = torch.relu(torch.randn(N_LABELED, EMB_DIM, device=dev, generator=gy))
     factored = kind == "badge"
+    g = torch.Generator(device=dev).manual_seed(1000)         # candidates and labeled rows: identical on every rank
+    X = torch.relu(torch.randn(N_ROWS, EMB_DIM, device=dev, generator=g))
+    gy = torch.Generator(device=dev).manual_seed(1)
+    Y = torch.relu(torch.randn(N_LABELED, EMB_DIM, device=dev, generator=gy))
     if factored:
-        lx = torch.randn(hi - lo, N_CLASSES, device=dev, generator=g) * 3
+        lx = torch.randn(N_ROWS, N_CLASSES, device=dev, generator=g) * 3
         ly = torch.randn(N_LABELED, N_CLASSES, device=dev, generator=gy) * 3
     rng = np.random.default_rng(0)
     us = rng.random(BUDGET)
-    vpos_all = torch.arange(N_LABELED, N_LABELED + N_ROWS, dtype=torch.int32, device=dev)
-    vpos = vpos_all[lo:hi].contiguous()
+    cand_pos = np.arange(N_LABELED, N_LABELED + N_ROWS, dtype=np.int32)
+    vpos = torch.as_tensor(cand_pos, device=dev)
+    full_n = N_ROWS + N_LABELED
+    shard_off = shard_pos = None
+    s0, s1 = 0, N_ROWS
+    if world > 1:
+        shard_off, shard_pos = plan_shards(cand_pos, full_n, world, leaf_aligned=factored)
+        s0, s1 = int(shard_off[rank]), int(shard_off[rank + 1])
+    n_loc = s1 - s0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     out = {}
-    n_loc = hi - lo
+    cpad = (N_CLASSES + 3) & ~3
+    XA_all = torch.empty((N_ROWS, cpad), device=dev) if factored else None
+    xan_all = torch.empty(N_ROWS, device=dev) if factored else None
 
-    def one(timed):
+    def one(timed, budget=BUDGET, sharded=True):
+        so, sp, a0, a1 = (shard_off, shard_pos, s0, s1) if sharded else (None, None, 0, N_ROWS)
         if world > 1:
             dist.barrier()
         if timed:
             ev[0].record()
         xn, yn = eng.row_norm2(X), eng.row_norm2(Y)
         XA = YA = xan = yan = None
-        if factored:
-            XA, xan = eng.badge_factors(lx, 128, row0=N_LABELED + lo, n_total=N_LABELED + N_ROWS)   # K2
-            YA, yan = eng.badge_factors(ly, 128, row0=0, n_total=N_LABELED + N_ROWS)
+        if factored:                                            # K2 over this rank's rows, then one all-gather
+            XA, xan = XA_all, xan_all
+            if sharded and world > 1:
+                sizes = [int(shard_off[q + 1] - shard_off[q]) for q in range(world)]
+                a_loc, an_loc = eng.badge_factors(lx[a0:a1], 128, row0=N_LABELED + a0, n_total=full_n)
+                if len(set(sizes)) == 1:
+                    dist.all_gather_into_tensor(XA_all, a_loc)
+                    dist.all_gather_into_tensor(xan_all, an_loc)
+                else:
+                    dist.all_gather([XA_all[int(shard_off[q]):int(shard_off[q + 1])] for q in range(world)], a_loc)
+                    dist.all_gather([xan_all[int(shard_off[q]):int(shard_off[q + 1])] for q in range(world)], an_loc)
+            else:
+                a_loc, an_loc = eng.badge_factors(lx, 128, row0=N_LABELED, n_total=full_n)
+                XA_all.copy_(a_loc)
+                xan_all.copy_(an_loc)
+            YA, yan = eng.badge_factors(ly, 128, row0=0, n_total=full_n)
         if timed:
             ev[1].record()
-        mind = eng.min_dist(X, xn, Y, yn, XA, xan, YA, yan)   # K3
+        mind = torch.full((N_ROWS,), float("inf"), device=dev)
+        sl = slice(a0, a1)
+        eng.min_dist(X[sl], xn[sl], Y, yn, XA[sl] if factored else None, xan[sl] if factored else None, YA, yan,
+                     out=mind[sl])                              # K3 over this rank's candidates
         if timed:
             ev[2].record()
-        picks, step_ms = eng.greedy_select(X, xn, mind, [0, n_loc], [BUDGET], a=XA, an=xan,
-                                           uniforms=us if factored else None, vpos=vpos if factored else None,
-                                           full_n=[N_ROWS + N_LABELED] if factored else None, time_steps=True,
-                                           shard_off=shard_off, vpos_all=vpos_all if (factored and world > 1) else None)
+        picks, stream_ms = eng.greedy_select(X, xn, mind, [0, N_ROWS], [budget], a=XA, an=xan,
+                                             uniforms=us[:budget] if factored else None, vpos=vpos if factored else None,
+                                             full_n=[full_n] if factored else None, time_steps=True,
+                                             shard_off=so, shard_pos=sp)
         if timed:
             ev[3].record()
             torch.cuda.synchronize()
             out["prep_ms"] = ev[0].elapsed_time(ev[1])
             out["k3_ms"] = ev[1].elapsed_time(ev[2])
             out["loop_ms"] = ev[2].elapsed_time(ev[3])
-            out["step_kernel_ms"] = step_ms
-            out["unique"] = len(set(picks.tolist())) == BUDGET
+            out["stream_ms"] = stream_ms
+            out["select_ms"] = eng.last_greedy_timing["select_ms"]
+            out["variant"] = eng.last_greedy_timing["variant"]
+            out["unique"] = len(set(picks.tolist())) == budget
         return picks
 
+    picks = None
     for _ in range(warmup):
-        one(False)
+        picks = one(False)
     tot, acc = 0.0, {}
     for _ in range(steps):
-        one(True)
-        for k in ("prep_ms", "k3_ms", "loop_ms", "step_kernel_ms"):
+        picks = one(True)
+        for k in ("prep_ms", "k3_ms", "loop_ms", "stream_ms", "select_ms"):
             acc[k] = acc.get(k, 0.0) + out[k]
         tot += out["prep_ms"] + out["k3_ms"] + out["loop_ms"]
     for k in acc:
         acc[k] /= steps
     ms = tot / steps
+    match = None
+    if world > 1 and check_picks > 0:                           # every rank: the same loop, unsharded, on its own GPU
+        ref = one(False, budget=check_picks, sharded=False)
+        same = torch.tensor([int(np.array_equal(ref, picks[:check_picks]))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        match = bool(same.item())
     if world > 1:       # device time of the slowest rank
-        t = torch.tensor([ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"], acc["step_kernel_ms"]], device=dev)
+        t = torch.tensor([ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"], acc["stream_ms"], acc["select_ms"]], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"], acc["step_kernel_ms"] = [float(v) for v in t]
+        ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"], acc["stream_ms"], acc["select_ms"] = [float(v) for v in t]
     row_bytes = 4 * EMB_DIM + 12 + (4 * N_CLASSES if factored else 0)
-    achieved = n_loc * row_bytes / (acc["step_kernel_ms"] * 1e-3) / 1e9
+    step_ms = acc["loop_ms"] / max(BUDGET - 1, 1)               # whole loop (setup, every barrier / exchange) per step
+    achieved = n_loc * row_bytes / (step_ms * 1e-3) / 1e9
+    achieved_stream = n_loc * row_bytes / (max(acc["stream_ms"], 1e-9) * 1e-3) / 1e9
     flops = 2.0 * n_loc * N_LABELED * (EMB_DIM + (N_CLASSES if factored else 0))
-    name = "step_pipe_kernel<factored,sample>" if factored else "step_pipe_kernel<dense,argmax>"
+    name = ("greedy_persist_kernel<factored,sample> (K5: TMA bulk-copy ring + LL-word agreement on the centre, one launch)"
+            if factored else "greedy_persist_kernel<dense,argmax> (K4, one persistent launch)")
     return {
         "workload": (f"BADGESampler tail (configs[3] shape, global k-means++ on rank-1 factors, {world} GPU)" if factored
                      else f"CoresetSampler tail (configs[2] shape, global greedy k-center, {world} GPU)"),
         "scaling": "strong" if world > 1 else None, "rows_per_gpu": n_loc,
-        "exchange": "peer-memory windows (CUDA IPC over NVLink), in-kernel, per step" if world > 1 else None,
+        "exchange": ("8-byte {tag,value} words over peer-memory windows (CUDA IPC / NVLink), inside the persistent kernel; "
+                     "rows replicated, a centre is a row id") if world > 1 else None,
         "candidates": N_ROWS, "labeled": N_LABELED, "budget": BUDGET, "dim": EMB_DIM,
         "classes": N_CLASSES if factored else None,
         "value": N_ROWS / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "picks_unique": out["unique"],
-        "breakdown_ms": acc,
+        "picks_match_single_gpu": match, "picks_checked": check_picks if match is not None else None,
+        "breakdown_ms": acc, "us_per_selection_step": step_ms * 1e3, "loop_variant": out.get("variant"),
         "roofline": {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "bytes_per_row_per_step": row_bytes,
-                     "traffic": ncu_traffic("step_factored_sample" if factored else "step_dense_argmax")},
+                     "timing": "loop time / (B - 1): CUDA events around the whole selection loop (one launch), so every "
+                               "barrier and exchange is inside",
+                     "streaming_phase": {"achieved": achieved_stream, "frac": achieved_stream / peak,
+                                         "us": acc["stream_ms"] * 1e3, "select_us": acc["select_ms"] * 1e3,
+                                         "timing": "%globaltimer stamps of CTA 0 inside the kernel"},
+                     "traffic": ncu_traffic("persist_factored_sample" if factored else "persist_dense_argmax")},
         "k3": {"kernel": "min_dist_tc_kernel (tcgen05 3xTF32 contraction, TMEM accumulators, fused min epilogue; "
                          "time includes the hi/lo operand split)",
                "bound": "tensor", "effective_fp32_tflops": flops / (acc["k3_ms"] * 1e-3) / 1e12,

@@ -46,7 +46,8 @@ void alq_destroy(alq_ctx* ctx);
 const char* alq_last_error(const alq_ctx* ctx);
 /* Implementation knobs (defaults pick the fastest valid kernel):
  *   "k3_impl"        0 auto | 1 exact-fp32 SIMT contraction | 2 tcgen05 3xTF32 contraction
- *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline
+ *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline | 3 persistent cooperative loop
+ *   "spin_timeout_ms" how long a kernel waits for a peer GPU's flag before giving up with ALQ_ERR_STATE (default 20000)
  *   "select_impl"    0 auto | 1 multi-kernel radix select   | 2 single cluster-resident launch
  *   "base_impl"      0 auto | 1 sequential class loop       | 2 per-class candidate lists + in-order resolve */
 int alq_set_option(alq_ctx* ctx, const char* key, int64_t value);
@@ -180,21 +181,35 @@ typedef struct alq_greedy_desc {
                                        first centre of a partition with nothing labeled, else -1 */
     /* output: [sum budget] partition-major, in pick order; row ids in [0, n) */
     int32_t* picks;
-    /* kernel variant: 0 = auto, 1 = direct-load, 2 = bulk-copy (TMA) pipeline */
+    /* kernel variant: 0 = auto, 1 = direct-load step kernel, 2 = bulk-copy (TMA) pipeline step kernel (one launch
+       per step), 3 = ONE persistent cooperative launch for the whole loop (TMA pipeline that keeps prefetching the
+       next step's rows while the grid agrees on the new centre).  Auto picks 3 whenever it fits. */
     int32_t variant;
-    /* multi-GPU (needs alq_comm_create/connect; n_parts must be 1): rows [shard_off[r], shard_off[r+1])
-       of the GLOBAL candidate list live on rank r; x/a/xn/an/mind/vpos describe this rank's rows only,
-       vpos_all (device, [shard_off[world]]) is every rank's vpos concatenated, picks are global row ids
-       and identical on every rank.  NULL => single GPU. */
+    /* multi-GPU (needs alq_comm_create/connect; n_parts must be 1; variant 3 only).  Every array above is indexed
+       by GLOBAL candidate row and REPLICATED on every rank (x/a/xn/an/vpos: n rows each; a few hundred MB next to
+       180 GB of HBM), so a new centre is announced as a row id and read locally -- no row payload crosses NVLink.
+       Rank r streams rows [shard_off[r], shard_off[r+1]) only and owns that range of `mind` (the rest of `mind` is
+       not touched).  picks are global row ids, identical on every rank.  NULL => single GPU.
+       D^2 sampling additionally needs the shards aligned to the leaves of NumPy's pairwise-sum tree over the
+       partition's full array: rank r's rows are exactly the candidates with vpos in
+       [shard_pos[r], shard_pos[r+1]), every shard_pos a leaf boundary (alq_pairwise_leaf_bounds), shard_pos[0] = 0,
+       shard_pos[world] = full_n[0].  Per step the ranks exchange 8-byte {tag, value} words through the peer-memory
+       windows (leaf sums, leaf masses, the pick): one-way NVLink stores, no fences, no collective library. */
     const int32_t* shard_off_host;
-    const int32_t* vpos_all;
-    /* optional: device events bracketing the streaming kernel are not exposed; instead the mean
-       duration of the streaming step kernel over this call is written here (ms), if non-NULL.
-       Forces a stream synchronisation at the end of the call. */
+    const int32_t* shard_pos_host;
+    /* optional timing out-parameter (forces a stream synchronisation at the end of the call), 4 floats in ms:
+       [0] mean time of the streaming phase of a step (variants 1/2: CUDA events around the step kernel; variant 3:
+       %globaltimer stamps taken by CTA 0), [1] mean time of the selection phase (barrier + exchange + draw) of a step
+       (variant 3 only), [2] steps measured, [3] the variant that ran. */
     float* step_kernel_ms_host;
 } alq_greedy_desc;
 
 int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* desc, void* stream);
+
+/* Leaf boundaries of NumPy's float32 pairwise summation over an array of n entries (blocks of <= 128 entries, splits
+ * at n/2 rounded down to a multiple of 8): out[0..k] ascending with out[0] = 0, out[k] = n.  Returns k (the number of
+ * leaves), or -1 if cap < k + 1.  Host-only helper for building leaf-aligned shards (alq_greedy_desc.shard_pos_host). */
+int64_t alq_pairwise_leaf_bounds(int64_t n, int32_t* out_host, int64_t cap);
 
 /* ---- K6: MASE / BASE ---------------------------------------------
  * mase_sampler.py:52-80 measures, for every pool row, the distance of its embedding h_i to the decision

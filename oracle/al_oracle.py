@@ -257,20 +257,41 @@ def d2_sampling_step(mind32: np.ndarray, labeled: np.ndarray, u: float) -> int:
 
 
 def coreset_streaming(feat: torch.Tensor, labeled_indicator: np.ndarray, query_count: int,
-                      randomize: bool = False, uniforms=None):
+                      randomize: bool = False, uniforms=None, factors: torch.Tensor = None, certificate=None):
     """Same picks as `coreset(pairwise_l2_dist(feat), ...)` but O(N) memory: running min of
     fl(fl(n_i+n_q) - 2*dot) against each new centre (min is exact, SURVEY.md finding 4).
     Used for the parity cases too large for a dense N x N matrix.  With `uniforms` given the
-    RNG is not touched."""
+    RNG is not touched.
+
+    factors: BADGE's second factor a[n, C].  The row of the reference's matrix is the gradient embedding
+    g_i = a_i (x) h_i (badge_sampler.py:40) with h = feat; it is rank-1 (SURVEY.md finding 6), so
+    <g_i, g_q> = <a_i, a_q> <h_i, h_q> and |g_i|^2 = |a_i|^2 |h_i|^2 and the 2048*1000-d rows are never formed
+    (at C = 1000, D = 2048 they cannot be: 8 MB per row).  On exact-arithmetic (small integer) fixtures this is
+    bit-identical to the materialised path (tests/test_oracle_golden.py pins the two against each other).
+
+    certificate: optional list; per step one float is appended -- arg-max: the gap between the largest and the
+    second-largest candidate min-distance (how far the pick is from a tie); D^2 draw: the distance of u from the
+    nearest cdf breakpoint.  A GPU path whose distances differ in the last bits can only diverge where it is tiny."""
     feat = feat.to(torch.float32).cpu()
     lab = np.array(labeled_indicator, dtype=bool, copy=True)
     n = feat.shape[0]
     sq = feat.square().sum(dim=1)
+    fa = None
+    if factors is not None:
+        fa = factors.to(torch.float32).cpu()
+        sq = sq * fa.square().sum(dim=1)
+
+    def dots(rows):                       # <g_i, g_j> for j in rows
+        dp = feat @ feat[rows].T if rows.dim() else feat @ feat[rows]
+        if fa is not None:
+            dp = dp * (fa @ fa[rows].T if rows.dim() else fa @ fa[rows])
+        return dp
+
     mind = torch.full((n,), float("inf"))
     lab_idx = np.flatnonzero(lab)
     for lo in range(0, len(lab_idx), 4096):
         j = torch.from_numpy(lab_idx[lo:lo + 4096])
-        d = (sq[:, None] + sq[j][None, :]) - 2 * (feat @ feat[j].T)
+        d = (sq[:, None] + sq[j][None, :]) - 2 * dots(j)
         mind = torch.minimum(mind, d.min(dim=1).values)
     picks = []
     for t in range(int(query_count)):
@@ -279,11 +300,21 @@ def coreset_streaming(feat: torch.Tensor, labeled_indicator: np.ndarray, query_c
         if randomize:
             u = float(uniforms[t]) if uniforms is not None else float(np.random.random_sample())
             q = d2_sampling_step(mind.numpy(), lab, u)
+            if certificate is not None:
+                prob = np.clip(mind.numpy(), 0, None)
+                prob[lab] = 0.0
+                cdf = (prob / np.sum(prob)).astype(np.float64).cumsum()
+                cdf /= cdf[-1]
+                near = [abs(cdf[q] - u)] + ([abs(u - cdf[q - 1])] if q > 0 else [])
+                certificate.append(float(min(near)))
         else:
             q = int(mind.max(dim=0).indices.item())
+            if certificate is not None:
+                top2 = torch.topk(mind, 2).values
+                certificate.append(float(top2[0] - top2[1]))
         picks.append(q)
         lab[q] = True
-        d = (sq + sq[q]) - 2 * (feat @ feat[q])
+        d = (sq + sq[q]) - 2 * dots(torch.tensor(q))
         mind = torch.minimum(mind, d)
     return picks
 

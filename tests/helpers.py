@@ -137,8 +137,18 @@ class OracleEngine:
         return torch.from_numpy((w & np.uint64(0xFFFFFFFF)).astype(np.int64).astype(np.int32))
 
     def badge_factors(self, logits, batch_size, row0=0, n_total=0):
-        assert row0 == 0 and n_total in (0, logits.shape[0])
-        a = O.badge_factors(logits, int(batch_size))
+        if n_total and (row0 or n_total != logits.shape[0]):
+            # a shard [row0, row0 + n) of a loader pass over n_total rows: 1/bs of the GLOBAL batch each row falls in
+            # (same closed form as O.badge_factors, badge_sampler.py:33-37)
+            n, bsz = logits.shape[0], int(batch_size)
+            g = np.arange(row0, row0 + n)
+            tail = n_total % bsz
+            bs_glob = np.where((tail > 0) & (g >= n_total - tail), tail, bsz).astype(np.float32)
+            lg = logits.detach().to(torch.float32).cpu()
+            onehot = torch.nn.functional.one_hot(lg.max(dim=1).indices, lg.shape[1]).to(torch.float32)
+            a = (torch.softmax(lg, dim=1) - onehot) / torch.from_numpy(bs_glob)[:, None]
+        else:
+            a = O.badge_factors(logits, int(batch_size))
         cpad = (a.shape[1] + 3) & ~3
         ap = torch.zeros((a.shape[0], cpad))
         ap[:, :a.shape[1]] = a
@@ -192,7 +202,20 @@ class OracleEngine:
         return torch.from_numpy(O.base_select(min_margin, radius, pred.long(), int(budget), radius.shape[1]).astype(np.int32))
 
     def greedy_select(self, x, xn, mind, part_off, budget, a=None, an=None, uniforms=None, vpos=None,
-                      full_n=None, first_pick=None, variant=0, time_steps=False):
+                      full_n=None, first_pick=None, variant=0, time_steps=False, shard_off=None, shard_pos=None):
+        if shard_off is not None:
+            # multi-rank protocol: arrays are global and replicated, every rank owns mind[shard]; the oracle engine
+            # simply gathers the shards of `mind` and runs the whole loop on every rank
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(), dist.get_rank()
+            parts = [None] * world
+            dist.all_gather_object(parts, mind[int(shard_off[rank]):int(shard_off[rank + 1])].clone())
+            mind = torch.cat(parts)
+            if shard_pos is not None:      # leaf-aligned shards: every rank's rows lie inside its position range
+                vp = vpos.numpy()
+                for r in range(world):
+                    seg = vp[int(shard_off[r]):int(shard_off[r + 1])]
+                    assert len(seg) == 0 or (seg.min() >= shard_pos[r] and seg.max() < shard_pos[r + 1])
         picks, u_at = [], 0
         nn_ = xn if a is None else xn * an
         for p in range(len(budget)):

@@ -84,3 +84,44 @@ def test_ctypes_argument_lists_match_the_header_prototypes():
         restype, argtypes = _lib.SIGNATURES[name]
         assert [kind_of_c(a) for a in args] == [kind_of_ctypes(t) for t in argtypes], name
         assert (restype is None) == (ret == "void"), name
+
+
+def test_pairwise_leaf_bounds_is_numpys_tree_and_matches_the_host_twin():
+    """alq_pairwise_leaf_bounds (host-only, callable without a GPU) against the Python twin used by the shard planner,
+    and against NumPy itself: summing float32 leaves left to right in NumPy's own blocking reproduces np.sum bit for bit
+    only if the leaves are the real ones."""
+    import numpy as np
+    from active_learning_b200 import _lib
+    from active_learning_b200.sharding import pairwise_leaf_bounds, plan_shards
+    lib = _lib.load()
+    for n in (1, 7, 128, 129, 1000, 13000, 130000, 130007):
+        out = np.empty(n // 64 + 8, dtype=np.int32)
+        k = lib.alq_pairwise_leaf_bounds(n, ctypes.c_void_p(out.ctypes.data), len(out))
+        twin = pairwise_leaf_bounds(n)
+        assert k == len(twin) - 1 and out[:k + 1].tolist() == twin.tolist()
+        assert twin[0] == 0 and twin[-1] == n and (np.diff(twin) <= 128).all() and (np.diff(twin) > 0).all()
+    assert lib.alq_pairwise_leaf_bounds(1000, ctypes.c_void_p(out.ctypes.data), 2) == -1
+    # the tree is NumPy's: fold the leaves' own np.sum values along the recursion and compare with np.sum
+    rng = np.random.default_rng(0)
+    x = rng.random(130007).astype(np.float32)
+
+    def fold(lo, m):
+        if m <= 128:
+            return np.sum(x[lo:lo + m])
+        half = m // 2
+        half -= half % 8
+        return np.float32(fold(lo, half) + fold(lo + half, m - half))
+
+    assert fold(0, len(x)) == np.sum(x)
+    # shard planner: leaf-aligned cuts, every candidate inside its rank's position range
+    cand = np.sort(rng.choice(130000, 80000, replace=False))
+    for world in (2, 3, 8):
+        off, pos = plan_shards(cand, 130000, world, leaf_aligned=True)
+        b = set(pairwise_leaf_bounds(130000).tolist())
+        assert all(int(p) in b for p in pos) and off[0] == 0 and off[-1] == len(cand)
+        for r in range(world):
+            seg = cand[off[r]:off[r + 1]]
+            assert len(seg) and seg.min() >= pos[r] and seg.max() < pos[r + 1]
+            assert abs(len(seg) - len(cand) / world) < 200
+    off, pos = plan_shards(cand, 130000, 4, leaf_aligned=False)
+    assert pos is None and off.tolist() == [0, 20000, 40000, 60000, 80000]

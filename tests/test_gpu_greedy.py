@@ -147,7 +147,7 @@ def test_min_dist_tensor_core_path(eng, n, m, d, c):
 
 
 # ------------------------------------------------------------------------------------------- K4 / K5 vs golden
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("tag", ["int", "f32"])
 def test_greedy_matches_reference_golden(eng, gold, tag, variant):
     feat, ind = torch.from_numpy(gold[f"cs_{tag}_feat"]), gold["cs_indicator"]
@@ -159,7 +159,7 @@ def test_greedy_matches_reference_golden(eng, gold, tag, variant):
         _assert_prefix_parity(got, ref, feat, ind, False)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("tag", ["int", "f32"])
 def test_d2_sampling_matches_reference_golden(eng, gold, tag, variant):
     feat, ind = torch.from_numpy(gold[f"cs_{tag}_feat"]), gold["cs_indicator"]
@@ -177,13 +177,15 @@ def test_cold_start_matches_reference_golden(eng, gold):
         xn = eng.row_norm2(X)
         q0 = eng.argmin(eng.min_dist(X, xn, X, xn, reduce_max=True))          # minimax centre
         assert q0 == int(gold[f"cs_{tag}_greedy_cold"][0])
-        assert _run(eng, feat, none, 6, first=q0) == gold[f"cs_{tag}_greedy_cold"].tolist()
+        for variant in (2, 3):
+            assert _run(eng, feat, none, 6, first=q0, variant=variant) == gold[f"cs_{tag}_greedy_cold"].tolist()
         np.random.seed(12)
         q0 = int(np.random.choice(len(feat)))
         us = np.zeros(6)
         us[1:] = np.random.random_sample(5)
-        assert _run(eng, feat, none, 6, randomize=True, uniforms=us, first=q0) == \
-            gold[f"cs_{tag}_d2sample_cold"].tolist()
+        for variant in (2, 3):
+            assert _run(eng, feat, none, 6, randomize=True, uniforms=us, first=q0, variant=variant) == \
+                gold[f"cs_{tag}_d2sample_cold"].tolist()
 
 
 def test_nan_retry_branch_matches_reference_golden(eng, gold):
@@ -191,7 +193,8 @@ def test_nan_retry_branch_matches_reference_golden(eng, gold):
     feat, ind = torch.from_numpy(gold["cs_dup_feat"]), gold["cs_dup_indicator"]
     np.random.seed(13)
     us = np.random.random_sample(5)
-    assert _run(eng, feat, ind, 5, randomize=True, uniforms=us) == gold["cs_dup_d2sample"].tolist()
+    for variant in (1, 2, 3):
+        assert _run(eng, feat, ind, 5, randomize=True, uniforms=us, variant=variant) == gold["cs_dup_d2sample"].tolist()
 
 
 # ------------------------------------------------------------------------------------------- larger, vs oracle
@@ -206,7 +209,7 @@ def test_greedy_exact_fixture_medium(eng, randomize, d):
     ind[rng.choice(n, l0, replace=False)] = True
     us = rng.random(b)
     ref = O.coreset_streaming(feat, ind, b, randomize=randomize, uniforms=us)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         assert _run(eng, feat, ind, b, randomize=randomize, uniforms=us, variant=variant) == ref
 
 
@@ -223,7 +226,8 @@ def test_d2_sampling_large_tree_exact(eng):
         us = rng.random(b)
         feat = h if a is None else (a[:, :, None] * h[:, None, :]).reshape(n + l0, -1)
         ref = O.coreset_streaming(feat, ind, b, randomize=True, uniforms=us)
-        assert _run(eng, h, ind, b, randomize=True, uniforms=us, factors=a) == ref
+        for variant in (2, 3):
+            assert _run(eng, h, ind, b, randomize=True, uniforms=us, factors=a, variant=variant) == ref
 
 
 def test_badge_factored_equals_materialised_reference(eng):
@@ -240,7 +244,7 @@ def test_badge_factored_equals_materialised_reference(eng):
     ref_rand = O.coreset(d2, ind, b, randomize=True)
     np.random.seed(3)
     us = np.random.random_sample(b)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         assert _run(eng, h, ind, b, randomize=True, uniforms=us, factors=a, variant=variant) == ref_rand
         assert _run(eng, h, ind, b, factors=a, variant=variant) == O.coreset(d2, ind, b)
 
@@ -272,16 +276,17 @@ def test_partitions_are_a_batch_dimension(eng):
             first.append(-1 if labs[p] else 17 + int(np.sum(sizes[:p])))
         Xall = torch.cat(X)
         off = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
-        picks = eng.greedy_select(Xall, eng.row_norm2(Xall), torch.cat(mind), off, budgets,
-                                  uniforms=np.concatenate(us) if randomize else None,
-                                  vpos=torch.as_tensor(np.concatenate(vpos).astype(np.int32)).cuda() if randomize else None,
-                                  full_n=[s + l for s, l in zip(sizes, labs)] if randomize else None,
-                                  first_pick=first)
-        at = 0
-        for p in range(4):
-            got = (picks[at:at + budgets[p]] - off[p] + labs[p]).tolist()
-            assert got == solo[p], (randomize, p)
-            at += budgets[p]
+        for variant in (2, 3):
+            picks = eng.greedy_select(Xall, eng.row_norm2(Xall), torch.cat(mind).clone(), off, budgets,
+                                      uniforms=np.concatenate(us) if randomize else None,
+                                      vpos=torch.as_tensor(np.concatenate(vpos).astype(np.int32)).cuda() if randomize else None,
+                                      full_n=[s + l for s, l in zip(sizes, labs)] if randomize else None,
+                                      first_pick=first, variant=variant)
+            at = 0
+            for p in range(4):
+                got = (picks[at:at + budgets[p]] - off[p] + labs[p]).tolist()
+                assert got == solo[p], (randomize, p, variant)
+                at += budgets[p]
 
 
 def test_full_size_coreset_properties(eng):
@@ -302,7 +307,8 @@ def test_full_size_coreset_properties(eng):
     m0 = mind.clone()
     picks1 = eng.greedy_select(X, xn, mind, [0, 80000], [b], variant=1)
     picks2 = eng.greedy_select(X, xn, m0.clone(), [0, 80000], [b], variant=2)
-    assert picks1.tolist() == picks2.tolist() and len(set(picks1.tolist())) == b
+    picks3 = eng.greedy_select(X, xn, m0.clone(), [0, 80000], [b], variant=3)
+    assert picks1.tolist() == picks2.tolist() == picks3.tolist() and len(set(picks1.tolist())) == b
     m = m0.clone()
     for t in range(b):
         mm = m.clone()
@@ -310,3 +316,54 @@ def test_full_size_coreset_properties(eng):
         q = int(torch.argmax(mm))                    # first max == lowest row on ties
         assert q == int(picks1[t]), t
         m = torch.minimum(m, (xn + xn[q]) - 2 * (X @ X[q]))
+
+
+# ------------------------------------------------------------------------------------------- BASELINE config 4 dimensions
+@pytest.mark.parametrize("randomize", [False, True])
+def test_factored_step_at_north_star_dimensions_exact(eng, randomize):
+    """The K5 / K4 step on rank-1 factors at C = 1000, D = 2048 (BASELINE config 4: 12 192-byte rows, 2 rows per
+    24 KB tile -- a different tile geometry from the small factored fixtures) on an exact-arithmetic fixture:
+    N = 6 000 rows, 900 labeled, 120 picks, against the oracle's factored streaming form (pinned to the
+    materialised reference path by tests/test_oracle_golden.py).  Every variant, identical lists."""
+    rng = np.random.default_rng(41 + randomize)
+    n, l0, b, c, d = 6000, 900, 120, 1000, 2048
+    h = torch.from_numpy(rng.integers(-1, 2, size=(n, d)).astype(np.float32))
+    a = torch.from_numpy(rng.integers(-1, 2, size=(n, c)).astype(np.float32))
+    ind = np.zeros(n, dtype=bool)
+    ind[rng.choice(n, l0, replace=False)] = True
+    us = rng.random(b)
+    ref = O.coreset_streaming(h, ind, b, randomize=randomize, uniforms=us, factors=a)
+    assert len(set(ref)) == b
+    for variant in (1, 2, 3):
+        assert _run(eng, h, ind, b, randomize=randomize, uniforms=us, factors=a, variant=variant) == ref, variant
+
+
+@pytest.mark.parametrize("randomize", [False, True])
+@pytest.mark.parametrize("c", [0, 1000])
+def test_float_fixture_d2048_with_gap_certificate(eng, randomize, c):
+    """SURVEY.md section 7 rung P1: float rows at d = 2048 (dense) and at C = 1000 x D = 2048 (factored).  The GPU
+    sums the dot products in a different order than MKL, so its distances differ from the oracle's in the last bits;
+    the oracle records, per step, how far its own decision was from flipping (arg-max: gap to the runner-up;
+    D^2 draw: distance of u from the nearest cdf breakpoint).  Picks must be identical up to the first step whose
+    certificate is below the rounding noise of fl(n_i + n_q - 2 dot) -- and that step, if any, must exist."""
+    g = torch.Generator().manual_seed(100 + 2 * c + randomize)
+    n, l0, b, d = 4000, 600, 80, 2048
+    h = torch.relu(torch.randn(n, d, generator=g))
+    a = None
+    if c:
+        z = torch.randn(n, c, generator=g) * 3
+        a = O.badge_factors(z, 128)
+    ind = np.zeros(n, dtype=bool)
+    ind[torch.randperm(n, generator=g)[:l0].numpy()] = True
+    us = np.random.default_rng(c + randomize).random(b)
+    cert = []
+    ref = O.coreset_streaming(h, ind, b, randomize=randomize, uniforms=us, factors=a, certificate=cert)
+    nsq = h.square().sum(1) * (a.square().sum(1) if a is not None else 1.0)
+    noise = 4e-6 * float(nsq.max()) * 2                     # a few ulps of n_i + n_q
+    for variant in (2, 3):
+        got = _run(eng, h, ind, b, randomize=randomize, uniforms=us, factors=a, variant=variant)
+        if got == ref:
+            continue
+        k = next(i for i, (x, y) in enumerate(zip(got, ref)) if x != y)
+        thr = noise if not randomize else noise / float(nsq.mean())     # cdf units: relative to the total mass
+        assert cert[k] <= thr, f"variant {variant}: picks diverge at step {k} whose certificate {cert[k]} > {thr}"

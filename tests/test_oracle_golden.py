@@ -174,3 +174,25 @@ def test_end_to_end_queries_match_reference(gold):
                 got = sorted(int(g) for g in got)
             key = f"e2e_{name}_{'sub' if sub else 'all'}_{etag}"
             assert got == gold[key].tolist(), key
+
+
+def test_factored_streaming_equals_materialised_rows():
+    """O.coreset_streaming(factors=...) -- the oracle form used at BASELINE config 4's dimensions, where the
+    2048*1000-d gradient embedding cannot be formed -- against the dense path on the materialised a (x) h rows
+    (badge_sampler.py:40), on exact-arithmetic fixtures: identical picks, both modes."""
+    rng = np.random.default_rng(9)
+    n, c, d, l0, b = 700, 8, 16, 100, 50
+    a = torch.from_numpy(rng.integers(-1, 2, size=(n, c)).astype(np.float32))
+    h = torch.from_numpy(rng.integers(-1, 2, size=(n, d)).astype(np.float32))
+    g = (a[:, :, None] * h[:, None, :]).reshape(n, -1)
+    ind = np.zeros(n, dtype=bool)
+    ind[rng.choice(n, l0, replace=False)] = True
+    us = rng.random(b)
+    dist = O.pairwise_l2_dist(g)
+    for randomize in (False, True):
+        cert = []
+        got = O.coreset_streaming(h, ind, b, randomize=randomize, uniforms=us, factors=a, certificate=cert)
+        assert got == O.coreset_streaming(g, ind, b, randomize=randomize, uniforms=us)
+        assert len(cert) == b and min(cert) >= 0.0
+        if not randomize:
+            assert got == O.coreset(dist, ind, b)

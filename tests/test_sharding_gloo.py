@@ -39,6 +39,23 @@ def _worker(rank, world, port, path, out_path):
         s._shard_group = group
         np.random.seed(21)
         res[name] = [int(i) for i in s.query(50.0)[0]]
+    # global CoreSet / BADGE: rows forwarded per rank, replicated by one all-gather, loop sharded by candidate row
+    # (leaf-aligned for the D^2 draw); incl. the cold start (nothing labeled)
+    for name, kw in (("CoresetSampler", {}), ("CoresetSampler", dict(subset_labeled=60, subset_unlabeled=300)),
+                     ("BADGESampler", dict(subset_labeled=60, subset_unlabeled=300))):
+        s = make_strategy(name, torch.from_numpy(gold["e2e_logits"]), torch.from_numpy(gold["e2e_emb_int"]),
+                          ev, lab, 64, engine=OracleEngine(), **kw)
+        s._shard_group = group
+        np.random.seed(21)
+        res[f"global_{name}_{'sub' if kw else 'all'}"] = [int(i) for i in s.query(50.0)[0]]
+    for name in ("CoresetSampler", "BADGESampler"):
+        for sharded in (True, False):
+            s = make_strategy(name, torch.from_numpy(gold["e2e_logits"]), torch.from_numpy(gold["e2e_emb_int"]),
+                              ev, [], 64, engine=OracleEngine())
+            if sharded:
+                s._shard_group = group
+            np.random.seed(5)
+            res[f"cold_{name}_{'multi' if sharded else 'single'}"] = [int(i) for i in s.query(12.0)[0]]
     # MASE rows sharded + merged; BASE margins sharded, class loop replicated on the gathered margins
     from helpers import HeadNet
     mg = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_mase.npz")))
@@ -74,6 +91,11 @@ def test_world_size_two_equals_single_process(gold):
     assert res["margin_f32_c10"] == gold["margin_f32_c10_picks"].tolist()
     assert res["PartitionedCoresetSampler"] == gold["e2e_PartitionedCoresetSampler_sub_int"].tolist()
     assert res["PartitionedBADGESampler"] == gold["e2e_PartitionedBADGESampler_sub_int"].tolist()
+    assert res["global_CoresetSampler_all"] == gold["e2e_CoresetSampler_all_int"].tolist()
+    assert res["global_CoresetSampler_sub"] == gold["e2e_CoresetSampler_sub_int"].tolist()
+    assert res["global_BADGESampler_sub"] == gold["e2e_BADGESampler_sub_int"].tolist()
+    for name in ("CoresetSampler", "BADGESampler"):
+        assert res[f"cold_{name}_multi"] == res[f"cold_{name}_single"] and len(res[f"cold_{name}_multi"]) == 12
     mg = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_mase.npz")))
     assert res["MASESampler"] == mg["a_mase_picks"].tolist()
     assert res["BASESampler"] == mg["a_base_picks"].tolist()

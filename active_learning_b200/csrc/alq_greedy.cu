@@ -951,6 +951,7 @@ extern "C" int alq_greedy_select(alq_ctx* ctx, const alq_greedy_desc* D, void* s
         D->step_kernel_ms_host[1] = 0.f;
         D->step_kernel_ms_host[2] = static_cast<float>(cnt);
         D->step_kernel_ms_host[3] = static_cast<float>(variant);
+        for (int i = 4; i < 8; ++i) D->step_kernel_ms_host[i] = 0.f;
     }
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
     if (status != 0) ALQ_FAIL(ctx, status, "alq_greedy_select: non-finite or empty probability mass during D^2 sampling");

@@ -28,8 +28,9 @@
 namespace {
 
 constexpr int kMaxLeaves = 4096;          // per partition: 2*K floats + K words of shared memory
-constexpr int kConsWarps = 16;
+constexpr int kConsWarps = 15;          // + 1 producer warp = 16 warps = 4 per SM sub-partition: 128 registers per thread
 constexpr int kConsThreads = kConsWarps * 32;
+constexpr int kGroups = kConsThreads / 8; // 8-lane groups per CTA == leaves a CTA can own
 
 struct PGroup {                 // one partition = one group of CTAs
     int cta_lo, ncta;
@@ -41,6 +42,8 @@ struct PGroup {                 // one partition = one group of CTAs
     int n_levels, level_base;   // level_off[level_base .. level_base + n_levels]
     int sched_base;             // sched[sched_base .. sched_base + n_leaves - 1): internal node j = (l | r << 16)
     int leaf_lo, leaf_hi;       // leaves summed by THIS rank
+    int seg_base, seg_stride;   // segtab[seg_base + r * seg_stride + cta] = first row of CTA `cta` of rank r
+    int ncta_base;              // ncta_of_rank[ncta_base + r] = CTAs rank r runs for this partition
     unsigned int keyw, leafw, massw, pickw;   // byte offsets of the LL regions inside a window
 };
 
@@ -52,31 +55,32 @@ struct PersistArgs {
     const int* vpos;
     const BlockSeg* segs;
     const PGroup* groups;
-    float* cfull;
+    unsigned long long* valw;      // [sum full_n] LL word per position of the full array: this step's min-distance
     const int* posinv;
     const int* leaf_off;
     const int* level_off;
     const unsigned int* sched;
+    const int* segtab;
+    const int* ncta_of_rank;
     const double* uniforms;
-    unsigned long long* best;      // [P * bmax]
-    unsigned int* ticket;          // [P * bmax]
-    unsigned int* bar;             // [P] monotonic rank-local barrier counter
     int* picks;
     int* status;
-    unsigned long long* prof;      // [4] ns: streaming, selection, steps, -
-    int bmax;
+    unsigned long long* prof;      // [8] ns: streaming, selection, steps, then selection sub-phases
     int world, rank;
     char* peer[ALQ_MAX_WORLD];     // windows (world == 1: peer[0] = local scratch)
     int leaf_bound[ALQ_MAX_WORLD + 1];   // multi-GPU D^2: rank r sums leaves [leaf_bound[r], leaf_bound[r+1])
     unsigned int ready_off;        // u64 ready[world] at the head of every window
     unsigned long long ready_tag;
-    unsigned int tag_base;         // (epoch & 0xff) << 24
+    unsigned int tag_base;         // 0x80000000 | (epoch & 0x7f) << 24
     long long timeout_cycles;
 };
 
 // ---- LL words --------------------------------------------------------------------------------------
 __device__ __forceinline__ void ll_store(void* p, unsigned int tag, unsigned int payload) {
     const unsigned long long v = (static_cast<unsigned long long>(tag) << 32) | payload;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ll_store_raw(void* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ll_load(const void* p) {
@@ -86,25 +90,65 @@ __device__ __forceinline__ unsigned long long ll_load(const void* p) {
 }
 // Bounded spin; after a failure anywhere (sticky status) every wait returns at once, so the loop drains
 // to its end in bounded time instead of hanging the GPU on a dead peer.
+__device__ __forceinline__ bool ll_give_up(int spin, long long t0, const PersistArgs& A) {
+    if ((spin & 63) != 63) return false;
+    if (*reinterpret_cast<volatile int*>(A.status) != 0) return true;
+    if (clock64() - t0 > A.timeout_cycles) { atomicCAS(A.status, 0, ALQ_ERR_STATE); return true; }
+    return false;
+}
 __device__ __forceinline__ unsigned int ll_wait(const void* p, unsigned int tag, const PersistArgs& A) {
     unsigned long long v = ll_load(p);
     if (static_cast<unsigned int>(v >> 32) == tag) return static_cast<unsigned int>(v);
     const long long t0 = clock64();
     for (int spin = 0;; ++spin) {
         v = ll_load(p);
-        if (static_cast<unsigned int>(v >> 32) == tag) break;
-        if ((spin & 63) == 63) {
-            if (*reinterpret_cast<volatile int*>(A.status) != 0) break;
-            if (clock64() - t0 > A.timeout_cycles) { atomicCAS(A.status, 0, ALQ_ERR_STATE); break; }
-        }
+        if (static_cast<unsigned int>(v >> 32) == tag || ll_give_up(spin, t0, A)) break;
     }
     return static_cast<unsigned int>(v);
 }
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// Collect `nwords` LL words at `base` (stride `stride` bytes) whose top (64 - shift) bits equal `tag`.
+// Polling is what floods L2 when 75 000 threads spin on words that are not there yet (measured: it slows the CTAs
+// that still stream and every store behind it), so it is rationed: only the first kPollers consumer threads poll;
+// (1) one warp spins on 32 sentinel words spread over the range -- one load per lane per round -- and only when
+// those have arrived (2) every poller loads its up-to-kBatch words as one batch (one L2 round trip), re-loading just
+// the few still missing.  Called by every consumer thread; the caller follows it with cons_bar().
+constexpr int kPollers = 256;
+constexpr int kBatch = 8;
+template <typename Sink>
+__device__ __forceinline__ void ll_gather(const char* base, int nwords, int stride, unsigned long long tag, int shift,
+                                          const PersistArgs& A, int ct, Sink&& sink) {
+    if (ct >= kPollers) return;
+    if (ct < 32 && nwords > 0) {
+        const char* sp = base + static_cast<size_t>(static_cast<long long>(ct) * nwords / 32) * stride;
+        const long long t0 = clock64();
+        for (int spin = 0; (ll_load(sp) >> shift) != tag; ++spin) {
+            if (ll_give_up(spin, t0, A)) break;
+            __nanosleep(40);
+        }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(kPollers) : "memory");
+    for (int chunk = 0; chunk < nwords; chunk += kPollers * kBatch) {
+        unsigned int pend = 0;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
+            if (chunk + ct + q * kPollers < nwords) pend |= 1u << q;
+        const long long t0 = clock64();
+        for (int spin = 0; pend; ++spin) {
+            unsigned long long w[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q)
+                if (pend & (1u << q)) w[q] = ll_load(base + static_cast<size_t>(chunk + ct + q * kPollers) * stride);
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q)
+                if ((pend & (1u << q)) && (w[q] >> shift) == tag) {
+                    sink(chunk + ct + q * kPollers, w[q]);
+                    pend &= ~(1u << q);
+                }
+            if (pend && ll_give_up(spin, t0, A)) break;
+        }
+    }
 }
+
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
 __device__ __forceinline__ unsigned long long gtime_ns() {
     unsigned long long t;
@@ -112,9 +156,34 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
     return t;
 }
 
+// NumPy pairwise_sum leaf (n <= 128) from registers: lane g of an 8-lane group holds a[8j + g] in v[j].
+//   r[g] = a[g]; r[g] += a[8i + g] for i = 1, 2, ..; ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)); then the n % 8 tail
+//   (n < 8: 0 + a[0] + a[1] + ..) added one by one.  prob = clip(min_dist, 0) (coreset_sampler.py:84).
+__device__ __forceinline__ float leaf_sum_regs(const float (&v)[16], int len, int lane, unsigned gmask) {
+    const int stop = len - (len & 7);
+    float r = 0.f;
+    if (stop > 0) {
+        r = fmaxf(v[0], 0.f);
+#pragma unroll
+        for (int j = 1; j < 16; ++j)
+            if (8 * j < stop) r += fmaxf(v[j], 0.f);
+        r = r + __shfl_down_sync(gmask, r, 1, 8);
+        r = r + __shfl_down_sync(gmask, r, 2, 8);
+        r = r + __shfl_down_sync(gmask, r, 4, 8);
+    }
+    const int jt = stop >> 3;                 // row of the tail elements a[stop + i] = lane i's v[jt]
+    float tv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j == jt) tv = fmaxf(v[j], 0.f);
+    const int g0 = lane & ~7;
+    for (int i = 0; i < (len & 7); ++i) r += __shfl_sync(gmask, tv, g0 + i);   // meaningful in the group's lane 0
+    return __shfl_sync(gmask, r, g0);
+}
+
 template <bool FACTORED, bool SAMPLE>
 __global__ void __launch_bounds__(32 * (1 + kConsWarps), 1)
-greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
+greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, const int lc_max) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int d = A.d, c = FACTORED ? A.c : 0;
     const int dv = d >> 2, cv = c >> 2;
@@ -126,13 +195,14 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
     double* sh_w = reinterpret_cast<double*>(sbest + kConsWarps);                             // [kConsWarps]
     float* val = reinterpret_cast<float*>(sh_w + kConsWarps);                                 // [2 * k_max] (SAMPLE)
     unsigned int* s_sched = reinterpret_cast<unsigned int*>(val + 2 * static_cast<size_t>(k_max));   // [k_max]
+    int* s_rows = reinterpret_cast<int*>(s_sched + k_max);                                    // [lc_max * 128] row of each owned position
     __shared__ int s_level[40];
     __shared__ int sh_centre, sh_hit, sh_nz;
     __shared__ double sh_base, sh_base_nz;
+    __shared__ unsigned long long s_prof[10];  // CTA 0 / thread 0 only: [0] stream [1] select [2..5] phases [6] step start [7] last stamp [8] stream end
 
     const BlockSeg seg = A.segs[blockIdx.x];
     const PGroup G = A.groups[seg.part];
-    const int p = seg.part;
     const int grank = static_cast<int>(blockIdx.x) - G.cta_lo;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = cfg.rows_per_tile;
@@ -196,12 +266,33 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
     const int ct = threadIdx.x - 32;          // 0 .. kConsThreads-1
     const int cw = warp - 1;
     const int C = cfg.consumers;              // warps that take tiles (<= kConsWarps)
-    const int cf_off = SAMPLE ? G.cfull_off : 0;
-    float* cf = A.cfull + cf_off;
     char* const win = A.peer[A.rank];
     const int K = G.n_leaves;
     const int root = K > 1 ? 2 * K - 2 : 0;
     const float4* q4 = reinterpret_cast<const float4*>(sq);
+    unsigned long long* const valw = A.valw + (SAMPLE ? G.cfull_off : 0);
+
+    // D^2 sampling: the leaf this 8-lane group owns for the whole call (one per group), the rows behind its
+    // positions (shared memory) and which of this lane's 16 positions hold a candidate at all
+    const int grp = ct >> 3, g_lane = ct & 7;
+    const unsigned gmask = 0xffu << ((lane >> 3) * 8);
+    int my_leaf = -1, leaf_pos = 0, leaf_len = 0;
+    unsigned int cand_mask = 0;
+    if (SAMPLE) {
+        const int leaf = G.leaf_lo + grank + grp * G.ncta;
+        if (leaf < G.leaf_hi) {
+            my_leaf = leaf;
+            leaf_pos = A.leaf_off[G.leaf_base + leaf];
+            leaf_len = A.leaf_off[G.leaf_base + leaf + 1] - leaf_pos;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = 8 * j + g_lane;
+                const int row = k < leaf_len ? A.posinv[G.cfull_off + leaf_pos + k] : -1;
+                s_rows[grp * 128 + k] = row;
+                if (row >= 0) cand_mask |= 1u << j;
+            }
+        }
+    }
 
     if (A.world > 1 && ct < A.world)          // peers may still be clearing their windows for this call
         for (long long t0 = clock64();;) {
@@ -212,20 +303,24 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
     cons_bar();
 
     // per-warp position in the tile stream (global over all steps): tiles cw, cw + C, cw + 2C, ...
-    long long my_it = cw;                     // next tile index (over all steps) this warp consumes
+    int my_i = cw;                            // next tile this warp consumes, relative to the current step's first tile
     int my_s = cw % cfg.stages;
     unsigned int my_par = 0;
     for (int q = cw / cfg.stages; q > 0; --q) my_par ^= 1u;
-    long long step_base = 0;                  // tile index of the first tile of the current step
 
-    unsigned int rnd_key = 0, rnd_leaf = 0, rnd_mass = 0, rnd_pick = 0, n_bar = 0;
+    unsigned int rnd_key = 0, rnd_leaf = 0, rnd_mass = 0, rnd_pick = 0;
     int centre = -1;
-    unsigned long long acc_stream = 0, acc_select = 0, t_a = 0, t_b = 0;
     const bool prof = A.prof != nullptr && blockIdx.x == 0 && ct == 0;
+    if (prof) for (int i = 0; i < 10; ++i) s_prof[i] = 0;
+    const int dbg_step = G.budget / 2;
+    unsigned long long* const dbg = (A.prof != nullptr && ct == 0) ? A.prof + 8 + 8 * blockIdx.x : nullptr;   // per-CTA stamps of one step
 
     for (int t = 0; t < G.budget; ++t) {
-        unsigned long long best_key = 0ull;
-        if (prof) t_a = gtime_ns();
+        unsigned long long best_key = 0ull;   // arg-max: ord(min-distance) << 32 | ~(row - seg.row_lo)
+        const unsigned int vtag = A.tag_base | (static_cast<unsigned int>(t + 1) & 0xffffffu);
+        double u = 0.0;
+        if (SAMPLE) u = __ldg(A.uniforms + G.pick_off + t);           // needed late: issue the load now
+        if (prof) s_prof[6] = gtime_ns();
         if (t == 0) {
             if (G.first_pick >= 0) {          // centre 0 chosen by the caller: no selection
                 centre = G.first_pick;
@@ -234,9 +329,9 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
             }
             for (int row = seg.row_lo + ct; row < seg.row_hi; row += kConsThreads) {
                 const float m = __ldcg(A.mind + row);
-                if (SAMPLE) cf[A.vpos[row]] = m;
+                if (SAMPLE) ll_store(valw + A.vpos[row], vtag, __float_as_uint(m));
                 else {
-                    const unsigned long long k = alq_maxkey(m, static_cast<uint32_t>(row));
+                    const unsigned long long k = (static_cast<unsigned long long>(alq_ord(m)) << 32) | (0xffffffffu - static_cast<uint32_t>(row - seg.row_lo));
                     best_key = k > best_key ? k : best_key;
                 }
             }
@@ -254,16 +349,16 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
             const float qn = FACTORED ? __ldg(A.xn + centre) * __ldg(A.an + centre) : __ldg(A.xn + centre);
             cons_bar();
             // ---- this step's tiles ----
-            const long long step_end = step_base + ntiles;
             if (cw < C) {
-                for (; my_it < step_end; my_it += C) {
-                    const int i = static_cast<int>(my_it - step_base);
-                    const int row0 = seg.row_lo + i * R;
+                for (; my_i < ntiles; my_i += C) {
+                    const int row0 = seg.row_lo + my_i * R;
                     const int rr = min(R, seg.row_hi - row0);
                     float m_old = 0.f, n_i = 0.f;
+                    int vp = 0;
                     if (lane < rr) {
                         m_old = __ldcg(A.mind + row0 + lane);
                         n_i = FACTORED ? __ldg(A.xn + row0 + lane) * __ldg(A.an + row0 + lane) : __ldg(A.xn + row0 + lane);
+                        if (SAMPLE) vp = __ldg(A.vpos + row0 + lane);
                     }
                     mbar_wait(&full[my_s], my_par);
                     const float* tx = tiles + static_cast<size_t>(my_s) * cfg.tile_floats;
@@ -305,9 +400,9 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
                         float m = fminf(m_old, dist_dense(n_i, qn, my_d2));
                         if (row == centre) m = ALQ_NEG_INF;         // a picked row is never a candidate again
                         __stcg(A.mind + row, m);
-                        if (SAMPLE) cf[A.vpos[row]] = m;            // raw running min; the draw clips at 0
+                        if (SAMPLE) ll_store(valw + vp, vtag, __float_as_uint(m));   // raw running min; the draw clips at 0
                         else {
-                            const unsigned long long k = alq_maxkey(m, static_cast<uint32_t>(row));
+                            const unsigned long long k = (static_cast<unsigned long long>(alq_ord(m)) << 32) | (0xffffffffu - static_cast<uint32_t>(row - seg.row_lo));
                             best_key = k > best_key ? k : best_key;
                         }
                     }
@@ -315,152 +410,162 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
                     if (my_s >= cfg.stages) { my_s -= cfg.stages; my_par ^= 1u; }
                 }
             }
-            step_base = step_end;
+            my_i -= ntiles;                   // the stream of tiles continues into the next step
         }
 
         // =================================== selection of pick t ===================================
         if (!SAMPLE) {
+            // every CTA of every rank publishes ONE word {tag16, row offset, ord}; everybody reads all of them
             best_key = warp_max_u64(best_key);
             if (lane == 0) sbest[cw] = best_key;
             cons_bar();
-            if (prof) t_b = gtime_ns();
+            if (prof) s_prof[8] = gtime_ns();
+            if (dbg && t == dbg_step) dbg[0] = gtime_ns();
+            const unsigned int tag16 = 0x8000u | ((A.tag_base >> 12) & 0x7000u) | (++rnd_key & 0xfffu);
+            const unsigned int slot = rnd_key & 1u;
+            const int stride = G.seg_stride;
             if (cw == 0) {
-                const unsigned int tag = A.tag_base | (++rnd_key & 0xffffffu);
-                const unsigned int slot = rnd_key & 1u;
-                int last = 0;
-                unsigned long long key = 0ull;
-                if (lane == 0) {
-                    unsigned long long b = 0ull;
-                    for (int w = 0; w < kConsWarps; ++w) b = sbest[w] > b ? sbest[w] : b;
-                    unsigned long long* bs = A.best + static_cast<size_t>(p) * A.bmax + t;
-                    if (b) atomicMax(bs, b);
-                    __threadfence();
-                    last = atomicAdd(A.ticket + static_cast<size_t>(p) * A.bmax + t, 1u) == static_cast<unsigned int>(G.ncta - 1);
-                    if (last) {
-                        __threadfence();
-                        key = *reinterpret_cast<volatile unsigned long long*>(bs);
+                unsigned long long b = lane < kConsWarps ? sbest[lane] : 0ull;
+                b = warp_max_u64(b);
+                const unsigned long long word = (static_cast<unsigned long long>(tag16) << 48) |
+                                                (static_cast<unsigned long long>((0xffffffffu - static_cast<uint32_t>(b)) & 0xffffu) << 32) | (b >> 32);
+                if (lane < A.world)
+                    ll_store_raw(A.peer[lane] + G.keyw + (static_cast<size_t>(slot) * A.world * stride + static_cast<size_t>(A.rank) * stride + grank) * 8, word);
+                if (grank == 0)               // slots of this rank beyond its CTA count (uneven shards): empty keys
+                    for (int e = G.ncta + (lane >> 3); e < stride; e += 4)
+                        if ((lane & 7) < A.world)
+                            ll_store_raw(A.peer[lane & 7] + G.keyw + (static_cast<size_t>(slot) * A.world * stride + static_cast<size_t>(A.rank) * stride + e) * 8,
+                                         static_cast<unsigned long long>(tag16) << 48);
+            }
+            unsigned long long k = 0ull;
+            ll_gather(win + G.keyw + static_cast<size_t>(slot) * A.world * stride * 8, A.world * stride, 8, tag16, 48, A, ct,
+                      [&](int i, unsigned long long w) {
+                          const uint32_t row = static_cast<uint32_t>(__ldg(A.segtab + G.seg_base + i)) + static_cast<uint32_t>((w >> 32) & 0xffffu);
+                          const unsigned long long key = (static_cast<unsigned long long>(static_cast<uint32_t>(w)) << 32) | (0xffffffffu - row);
+                          k = key > k ? key : k;
+                      });
+            cons_bar();                       // sbest is reused
+            k = warp_max_u64(k);
+            if (lane == 0) sbest[cw] = k;
+            cons_bar();
+            unsigned long long kk = sbest[0];
+#pragma unroll
+            for (int w = 1; w < kConsWarps; ++w) kk = sbest[w] > kk ? sbest[w] : kk;
+            centre = static_cast<int>(alq_maxkey_row(kk));
+        } else {
+            if (prof) s_prof[8] = gtime_ns();
+            if (dbg && t == dbg_step) dbg[0] = gtime_ns();
+            // ---- (1) this group's leaf: wait for this step's min-distance of every candidate position ----
+            float v[16];
+            {
+                // all loads of a round are issued before any tag is looked at: one L2 round trip per round, not 16
+                unsigned int pend = cand_mask;
+                const unsigned long long* base = valw + leaf_pos + g_lane;
+                const long long t0 = clock64();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = ALQ_NEG_INF;          // labeled / padding positions: prob 0
+                if (pend) {                   // one word per lane until it is there: no flood while the rows still stream
+                    const unsigned long long* sp = base + 8 * (31 - __clz(pend));
+                    for (int spin = 0; static_cast<unsigned int>(ll_load(sp) >> 32) != vtag; ++spin) {
+                        if (ll_give_up(spin, t0, A)) break;
+                        __nanosleep(40);
                     }
                 }
-                last = __shfl_sync(0xffffffffu, last, 0);
-                key = __shfl_sync(0xffffffffu, key, 0);
-                if (last && lane < A.world) {     // this rank's best -> every rank (two LL words)
-                    char* dst = A.peer[lane] + G.keyw + (static_cast<size_t>(slot) * A.world + A.rank) * 16;
-                    ll_store(dst, tag, static_cast<unsigned int>(key >> 32));
-                    ll_store(dst + 8, tag, static_cast<unsigned int>(key));
+                for (int spin = 0; pend; ++spin) {
+                    unsigned long long w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (pend & (1u << j)) w[j] = ll_load(base + 8 * j);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if ((pend & (1u << j)) && static_cast<unsigned int>(w[j] >> 32) == vtag) {
+                            v[j] = __uint_as_float(static_cast<unsigned int>(w[j]));
+                            pend &= ~(1u << j);
+                        }
+                    if (pend && ll_give_up(spin, t0, A)) break;
                 }
-                unsigned long long k = 0ull;
-                if (lane < A.world) {
-                    const char* src = win + G.keyw + (static_cast<size_t>(slot) * A.world + lane) * 16;
-                    const unsigned int hi = ll_wait(src, tag, A);
-                    const unsigned int lo = ll_wait(src + 8, tag, A);
-                    k = (static_cast<unsigned long long>(hi) << 32) | lo;
-                }
-                k = warp_max_u64(k);
-                if (lane == 0) sh_centre = static_cast<int>(alq_maxkey_row(k));
             }
-            cons_bar();
-            centre = sh_centre;
-        } else {
-            // ---- (1) every min-distance of this rank's rows is in cfull ----
-            cons_bar();
-            if (prof) t_b = gtime_ns();
+            if (prof) { const unsigned long long x0 = gtime_ns(); s_prof[2] += x0 - s_prof[8]; s_prof[7] = x0; }
+            if (dbg && t == dbg_step) dbg[1] = gtime_ns();
             float total32 = 0.f;
             bool failed = false;
             for (int attempt = 0;; ++attempt) {
-                if (ct == 0) {
-                    __threadfence();
-                    atomicAdd(A.bar + p, 1u);
-                    const unsigned int target = static_cast<unsigned int>(G.ncta) * (++n_bar);
-                    const long long t0 = clock64();
-                    for (int spin = 0; static_cast<int>(ld_acquire_gpu_u32(A.bar + p) - target) < 0; ++spin)
-                        if ((spin & 63) == 63 && (*reinterpret_cast<volatile int*>(A.status) != 0 || clock64() - t0 > A.timeout_cycles)) {
-                            atomicCAS(A.status, 0, ALQ_ERR_STATE);
-                            break;
+                // ---- (2) leaf sums of NumPy's pairwise tree -> every rank; fold the tree in shared memory ----
+                const unsigned int tag = A.tag_base | (++rnd_leaf & 0xffffffu);
+                const unsigned int slot = rnd_leaf & 1u;
+                if (my_leaf >= 0) {
+                    const float s = leaf_sum_regs(v, leaf_len, lane, gmask);
+                    if (g_lane < A.world)
+                        ll_store(A.peer[g_lane] + G.leafw + (static_cast<size_t>(slot) * K + my_leaf) * 8, tag, __float_as_uint(s));
+                }
+                ll_gather(win + G.leafw + static_cast<size_t>(slot) * K * 8, K, 8, tag, 32, A, ct,
+                          [&](int i, unsigned long long w) { val[i] = __uint_as_float(static_cast<unsigned int>(w)); });
+                cons_bar();
+                {
+                    int h = 0;
+                    for (; h < G.n_levels && s_level[h + 1] - s_level[h] > 32; ++h) {     // wide levels: the whole block
+                        const int lo = s_level[h], hi = s_level[h + 1];
+                        for (int j = lo + ct; j < hi; j += kConsThreads) {
+                            const unsigned int e = s_sched[j];
+                            val[K + j] = val[e & 0xffffu] + val[e >> 16];
+                        }
+                        cons_bar();
+                    }
+                    if (cw == 0)                                                          // the top of the tree: one warp
+                        for (; h < G.n_levels; ++h) {
+                            const int lo = s_level[h], hi = s_level[h + 1];
+                            for (int j = lo + lane; j < hi; j += 32) {
+                                const unsigned int e = s_sched[j];
+                                val[K + j] = val[e & 0xffffu] + val[e >> 16];
+                            }
+                            __syncwarp();
                         }
                 }
                 cons_bar();
-                // ---- (2) leaf sums of NumPy's pairwise tree: one 8-lane group per leaf ----
-                const unsigned int tag = A.tag_base | (++rnd_leaf & 0xffffffu);
-                const unsigned int slot = rnd_leaf & 1u;
-                {
-                    const int grp = ct >> 3, g_lane = ct & 7;
-                    const unsigned gmask = 0xffu << ((lane >> 3) * 8);
-                    for (int lf = grp;; lf += kConsThreads / 8) {
-                        const int leaf = G.leaf_lo + grank + lf * G.ncta;
-                        if (leaf >= G.leaf_hi) break;
-                        const int lo = A.leaf_off[G.leaf_base + leaf], len = A.leaf_off[G.leaf_base + leaf + 1] - lo;
-                        float v = leaf_sum_group(cf + lo, len, g_lane, gmask);
-                        v = __shfl_sync(gmask, v, lane & ~7);
-                        if (g_lane < A.world)
-                            ll_store(A.peer[g_lane] + G.leafw + (static_cast<size_t>(slot) * K + leaf) * 8, tag, __float_as_uint(v));
-                    }
-                }
-                for (int i = ct; i < K; i += kConsThreads)
-                    val[i] = __uint_as_float(ll_wait(win + G.leafw + (static_cast<size_t>(slot) * K + i) * 8, tag, A));
-                cons_bar();
-                for (int h = 0; h < G.n_levels; ++h) {
-                    const int lo = s_level[h], hi = s_level[h + 1];
-                    for (int j = lo + ct; j < hi; j += kConsThreads) {
-                        const unsigned int e = s_sched[j];
-                        val[K + j] = val[e & 0xffffu] + val[e >> 16];
-                    }
-                    cons_bar();
-                }
                 total32 = val[root];
                 cons_bar();                                   // val is reused below
                 if (total32 > 0.f && total32 <= 3.4028234e38f) break;
                 if (!(total32 == 0.f) || attempt > (1 << 20)) { failed = true; break; }   // NaN / inf mass
-                // sum == 0 -> prob is NaN -> `min_dist_labeled += 0.00001` and retry (:87-90).  In place: the next
-                // step rewrites every candidate slot from `mind`, so the bump never outlives this draw.
-                for (int row = seg.row_lo + ct; row < seg.row_hi; row += kConsThreads) {
-                    float* q = cf + A.vpos[row];
-                    __stcg(q, __ldcg(q) + 0.00001f);
-                }
-                cons_bar();
+                // sum == 0 -> prob is NaN -> `min_dist_labeled += 0.00001` and retry (:87-90): on the register copy of
+                // this step's values, so the bump never outlives this draw (the next step brings fresh values)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += 0.00001f;
             }
+            if (prof) { const unsigned long long x1 = gtime_ns(); s_prof[3] += x1 - s_prof[7]; s_prof[7] = x1; }
+            if (dbg && t == dbg_step) dbg[2] = gtime_ns();
             if (failed) {                                     // the same decision in every CTA of every rank
                 if (ct == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
                 centre = G.row_lo;
             } else {
-                // ---- (3) fp64 mass of prob = clip(mind, 0) / S per leaf ----
+                // ---- (3) fp64 mass of prob = clip(mind, 0) / S per leaf -> every rank ----
                 const unsigned int tag = A.tag_base | (++rnd_mass & 0xffffffu);
                 const unsigned int slot = rnd_mass & 1u;
-                {
-                    const int grp = ct >> 3, g_lane = ct & 7;
-                    const unsigned gmask = 0xffu << ((lane >> 3) * 8);
-                    for (int lf = grp;; lf += kConsThreads / 8) {
-                        const int leaf = G.leaf_lo + grank + lf * G.ncta;
-                        if (leaf >= G.leaf_hi) break;
-                        const int lo = A.leaf_off[G.leaf_base + leaf], len = A.leaf_off[G.leaf_base + leaf + 1] - lo;
-                        float v[16];
+                if (my_leaf >= 0) {
+                    double m = 0.0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = (8 * j + g_lane < len) ? __ldcg(cf + lo + 8 * j + g_lane) : 0.f;
-                        double m = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) m += prob64(v[j], total32);
-                        m += __shfl_down_sync(gmask, m, 1, 8);
-                        m += __shfl_down_sync(gmask, m, 2, 8);
-                        m += __shfl_down_sync(gmask, m, 4, 8);
-                        m = __shfl_sync(gmask, m, lane & ~7);
-                        if (g_lane < A.world) {
-                            char* dst = A.peer[g_lane] + G.massw + (static_cast<size_t>(slot) * K + leaf) * 16;
-                            ll_store(dst, tag, static_cast<unsigned int>(__double2hiint(m)));
-                            ll_store(dst + 8, tag, static_cast<unsigned int>(__double2loint(m)));
-                        }
+                    for (int j = 0; j < 16; ++j) m += prob64(v[j], total32);
+                    m += __shfl_down_sync(gmask, m, 1, 8);
+                    m += __shfl_down_sync(gmask, m, 2, 8);
+                    m += __shfl_down_sync(gmask, m, 4, 8);
+                    m = __shfl_sync(gmask, m, lane & ~7);
+                    if (g_lane < A.world) {
+                        char* dst = A.peer[g_lane] + G.massw + (static_cast<size_t>(slot) * K + my_leaf) * 16;
+                        ll_store(dst, tag, static_cast<unsigned int>(__double2hiint(m)));
+                        ll_store(dst + 8, tag, static_cast<unsigned int>(__double2loint(m)));
                     }
                 }
+                if (dbg && t == dbg_step) dbg[3] = gtime_ns();
                 double* M = reinterpret_cast<double*>(val);   // K doubles == 2K floats
-                for (int i = ct; i < K; i += kConsThreads) {
-                    const char* src = win + G.massw + (static_cast<size_t>(slot) * K + i) * 16;
-                    const unsigned int hi = ll_wait(src, tag, A);
-                    const unsigned int lo = ll_wait(src + 8, tag, A);
-                    M[i] = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+                {
+                    unsigned int* M32 = reinterpret_cast<unsigned int*>(M);      // word 2i = hi, 2i + 1 = lo of leaf i
+                    ll_gather(win + G.massw + static_cast<size_t>(slot) * K * 16, 2 * K, 8, tag, 32, A, ct,
+                              [&](int i, unsigned long long w) { M32[i ^ 1] = static_cast<unsigned int>(w); });   // little endian: lo first
                 }
+                if (dbg && t == dbg_step) dbg[4] = gtime_ns();
                 if (ct == 0) { sh_hit = 0x7fffffff; sh_nz = -1; }
                 cons_bar();
                 // ---- np.random.choice == first k with cumsum64(p)[k] / total > u: locate the leaf.  One fixed
                 //      chain (thread chunks -> lanes -> warps), identical in every CTA of every rank. ----
-                const double u = A.uniforms[G.pick_off + t];
                 const int per = (K + kConsThreads - 1) / kConsThreads;
                 const int l0 = min(K, ct * per), l1 = min(K, l0 + per);
                 double loc = 0.0;
@@ -468,8 +573,8 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
                 double inc = loc;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const double v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
+                    const double w = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += w;
                 }
                 if (lane == 31) sh_w[cw] = inc;
                 const double prev = __shfl_up_sync(0xffffffffu, inc, 1);
@@ -488,8 +593,13 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
                     if (M[l] > 0.0) { my_nz = l; nz_base = before; }
                     if (my_hit == 0x7fffffff && (run / total) > u) { my_hit = l; hit_base = before; }
                 }
-                if (my_hit != 0x7fffffff) atomicMin(&sh_hit, my_hit);
-                if (my_nz >= 0) atomicMax(&sh_nz, my_nz);
+                {
+                    const int wh = __reduce_min_sync(0xffffffffu, my_hit), wn = __reduce_max_sync(0xffffffffu, my_nz);
+                    if (lane == 0) {
+                        if (wh != 0x7fffffff) atomicMin(&sh_hit, wh);
+                        if (wn >= 0) atomicMax(&sh_nz, wn);
+                    }
+                }
                 cons_bar();
                 if (my_hit != 0x7fffffff && my_hit == sh_hit) sh_base = hit_base;
                 if (my_nz >= 0 && my_nz == sh_nz) sh_base_nz = nz_base;
@@ -497,74 +607,68 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max) {
                 int leaf = sh_hit;
                 double base = sh_base;
                 if (leaf == 0x7fffffff) { leaf = sh_nz; base = sh_base_nz; }   // u beyond the last mass by an ulp
-                // ---- (4) the CTA that owns the leaf searches inside it and announces the row ----
+                if (prof) { const unsigned long long x2 = gtime_ns(); s_prof[4] += x2 - s_prof[7]; s_prof[7] = x2; }
+                if (dbg && t == dbg_step) dbg[5] = gtime_ns();
+                // ---- (4) the group that owns the leaf searches inside it (values still in registers) ----
                 const unsigned int ptag = A.tag_base | (++rnd_pick & 0xffffffu);
                 const unsigned int pslot = rnd_pick & 1u;
-                int owner_rank = 0;
-                for (int r = 1; r < A.world; ++r)
-                    if (leaf >= A.leaf_bound[r]) owner_rank = r;
-                const bool mine = leaf >= 0 && owner_rank == A.rank && (leaf - G.leaf_lo) % G.ncta == grank;
                 if (leaf < 0 && grank == 0 && A.rank == 0 && cw == 0) {       // no mass at all: cannot happen with S > 0
                     if (lane == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
                     if (lane < A.world) ll_store(A.peer[lane] + G.pickw + pslot * 8, ptag, static_cast<unsigned int>(G.row_lo));
                 }
-                if (mine && cw == 0) {
-                    const int lo = A.leaf_off[G.leaf_base + leaf], len = A.leaf_off[G.leaf_base + leaf + 1] - lo;
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = (4 * lane + j < len) ? __ldcg(cf + lo + 4 * lane + j) : 0.f;
-                    double pl[4], lsum = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { pl[j] = prob64(v[j], total32); lsum += pl[j]; }
-                    double linc = lsum;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const double w = __shfl_up_sync(0xffffffffu, linc, o);
-                        if (lane >= o) linc += w;
-                    }
-                    double r2 = base + (linc - lsum);
+                if (leaf >= 0 && leaf == my_leaf) {           // whole 8-lane group, uniformly
+                    // sequential order k = 8j + lane: scan 8 lanes per j, carry across j
+                    double carry = base;
                     int hit = -1, nz = -1;
+                    const int g0 = lane & ~7;
+                    for (int j = 0; j < 16 && 8 * j < leaf_len; ++j) {
+                        double pj = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        r2 += pl[j];
-                        if (pl[j] > 0.0) nz = 4 * lane + j;
-                        if (hit < 0 && 4 * lane + j < len && (r2 / total) > u) hit = 4 * lane + j;
+                        for (int jj = 0; jj < 16; ++jj)
+                            if (jj == j) pj = prob64(v[jj], total32);
+                        double sc = pj;
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) {
+                            const double w = __shfl_up_sync(gmask, sc, o, 8);
+                            if (g_lane >= o) sc += w;
+                        }
+                        const double rk = carry + sc;
+                        const bool cross = pj > 0.0 ? ((rk / total) > u) : false;
+                        // an element with zero mass can cross only if an earlier one did: ignore it
+                        const unsigned cb = (__ballot_sync(gmask, cross) >> g0) & 0xffu;
+                        const unsigned zb = (__ballot_sync(gmask, pj > 0.0) >> g0) & 0xffu;
+                        if (zb) nz = 8 * j + (31 - __clz(zb));
+                        if (cb) { hit = 8 * j + (__ffs(cb) - 1); break; }
+                        carry = __shfl_sync(gmask, rk, g0 + 7);
                     }
-                    const unsigned hb = __ballot_sync(0xffffffffu, hit >= 0);
-                    int k;
-                    if (hb) k = __shfl_sync(0xffffffffu, hit, __ffs(hb) - 1);
-                    else {                                   // re-association moved the crossing by an ulp
-                        const unsigned nb = __ballot_sync(0xffffffffu, nz >= 0);
-                        k = nb ? __shfl_sync(0xffffffffu, nz, 31 - __clz(nb)) : -1;
-                    }
-                    int row = k >= 0 ? A.posinv[cf_off + lo + k] : -1;
+                    const int k = hit >= 0 ? hit : nz;        // no crossing: re-association moved it by an ulp
+                    int row = k >= 0 ? s_rows[grp * 128 + k] : -1;
                     if (row < 0) {
-                        if (lane == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
+                        if (g_lane == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
                         row = G.row_lo;
                     }
-                    if (lane < A.world) ll_store(A.peer[lane] + G.pickw + pslot * 8, ptag, static_cast<unsigned int>(row));
+                    if (g_lane < A.world) ll_store(A.peer[g_lane] + G.pickw + pslot * 8, ptag, static_cast<unsigned int>(row));
+                    if (A.prof != nullptr && g_lane == 0 && t == dbg_step) A.prof[8 + 8 * blockIdx.x + 6] = gtime_ns();
                 }
                 if (ct == 0) sh_centre = static_cast<int>(ll_wait(win + G.pickw + pslot * 8, ptag, A));
                 cons_bar();
                 centre = sh_centre;
+                if (prof) { const unsigned long long x3 = gtime_ns(); s_prof[5] += x3 - s_prof[7]; }
             }
         }
         if (grank == 0 && ct == 0) A.picks[G.pick_off + t] = centre;
+        if (dbg && t == dbg_step) dbg[7] = gtime_ns();
         if (prof) {
             const unsigned long long t_c = gtime_ns();
-            if (t > 0) { acc_stream += t_b - t_a; acc_select += t_c - t_b; }
+            if (t > 0) { s_prof[0] += s_prof[8] - s_prof[6]; s_prof[1] += t_c - s_prof[8]; }
         }
     }
     if (prof) {
-        A.prof[0] = acc_stream;
-        A.prof[1] = acc_select;
+        A.prof[0] = s_prof[0];
+        A.prof[1] = s_prof[1];
         A.prof[2] = static_cast<unsigned long long>(G.budget > 1 ? G.budget - 1 : 0);
+        for (int i = 0; i < 4; ++i) A.prof[3 + i] = s_prof[2 + i];
     }
-}
-
-__global__ void persist_fill_kernel(float* p, int n, float v) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
 }
 
 // posinv[off[p] + vpos[row]] = row for every candidate row of every partition
@@ -605,11 +709,11 @@ struct PairTree {
 };
 
 template <bool FACTORED, bool SAMPLE>
-cudaError_t launch_persist(int grid, size_t smem, cudaStream_t st, PersistArgs& A, PipeCfg& cfg, int& k_max) {
+cudaError_t launch_persist(int grid, size_t smem, cudaStream_t st, PersistArgs& A, PipeCfg& cfg, int& k_max, int& lc_max) {
     auto* fn = greedy_persist_kernel<FACTORED, SAMPLE>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    void* args[] = {&A, &cfg, &k_max};
+    void* args[] = {&A, &cfg, &k_max, &lc_max};
     return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fn), dim3(grid), dim3(32 * (1 + kConsWarps)), args, smem, st);
 }
 
@@ -640,8 +744,6 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     // ---- does the problem fit? --------------------------------------------------------------------------
     const size_t row_bytes = static_cast<size_t>(d + c) * 4;
     if ((row_bytes % 16) || (static_cast<size_t>(d) * 4 % 16)) return kPersistNotApplicable;
-    int row_lo = 0, row_hi = static_cast<int>(n);
-    if (comm) { row_lo = D->shard_off_host[rank]; row_hi = D->shard_off_host[rank + 1]; }
     std::vector<int> pick_off(P + 1, 0);
     int bmax = 0, active = 0;
     for (int p = 0; p < P; ++p) {
@@ -652,21 +754,81 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     if (active == 0) return ALQ_OK;
     if (active > ctx->sm_count) return kPersistNotApplicable;
 
-    // ---- trees (D^2 sampling) ------------------------------------------------------------------------------
+    // ---- CTAs: at most one per SM in total, split over the partitions by row count.  In multi-GPU mode (P == 1)
+    //      every rank derives every rank's segmentation (the arg-max words carry a row offset inside a segment). ----
     std::vector<PGroup> groups(P);
+    std::vector<BlockSeg> segs;
+    std::vector<int> segtab, ncta_tab;
+    {
+        std::vector<int64_t> rows(P, 0);
+        int64_t total = 0;
+        for (int p = 0; p < P; ++p) {
+            if (D->budget_host[p] <= 0) continue;
+            rows[p] = comm ? (D->shard_off_host[rank + 1] - D->shard_off_host[rank]) : (D->part_off_host[p + 1] - D->part_off_host[p]);
+            total += rows[p];
+        }
+        int left = ctx->sm_count - active;           // one CTA per active partition first, the rest by share
+        std::vector<int> nb(P, 0);
+        for (int p = 0; p < P; ++p) {
+            if (D->budget_host[p] <= 0) continue;
+            const int extra = total > 0 ? static_cast<int>(static_cast<int64_t>(ctx->sm_count - active) * rows[p] / total) : 0;
+            nb[p] = 1 + std::min(extra, left);
+            left -= nb[p] - 1;
+        }
+        for (int p = 0; p < P && left > 0; ++p)
+            if (nb[p] > 0 && rows[p] > nb[p]) { ++nb[p]; --left; }
+        auto ncta_for = [&](int want, int64_t r) { return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, std::max<int64_t>(r, 1)))); };
+        int cta = 0;
+        for (int p = 0; p < P; ++p) {
+            PGroup& g = groups[p];
+            g = PGroup{};
+            g.budget = D->budget_host[p];
+            g.pick_off = pick_off[p];
+            g.first_pick = D->first_pick_host ? D->first_pick_host[p] : -1;
+            g.row_lo = comm ? 0 : D->part_off_host[p];
+            g.n_leaves = 1;
+            if (nb[p] == 0) continue;
+            g.seg_base = static_cast<int>(segtab.size());
+            g.ncta_base = static_cast<int>(ncta_tab.size());
+            int stride = 0;
+            for (int r = 0; r < world; ++r) {
+                const int64_t rr = comm ? (D->shard_off_host[r + 1] - D->shard_off_host[r]) : rows[p];
+                const int k = ncta_for(comm ? ctx->sm_count : nb[p], rr);
+                ncta_tab.push_back(k);
+                stride = std::max(stride, k);
+            }
+            g.seg_stride = stride;
+            segtab.resize(segtab.size() + static_cast<size_t>(world) * stride, 0);
+            for (int r = 0; r < world; ++r) {
+                const int lo = comm ? D->shard_off_host[r] : D->part_off_host[p];
+                const int64_t rr = comm ? (D->shard_off_host[r + 1] - D->shard_off_host[r]) : rows[p];
+                const int k = ncta_tab[g.ncta_base + r];
+                for (int b = 0; b < k; ++b) {
+                    const int s_lo = lo + static_cast<int>(rr * b / k), s_hi = lo + static_cast<int>(rr * (b + 1) / k);
+                    segtab[g.seg_base + static_cast<size_t>(r) * stride + b] = s_lo;
+                    if (!sample && s_hi - s_lo > 65535) return kPersistNotApplicable;   // 16-bit row offset in the key word
+                    if (r == rank) {
+                        BlockSeg s;
+                        s.row_lo = s_lo; s.row_hi = s_hi; s.part = p; s.pad = 0;
+                        segs.push_back(s);
+                    }
+                }
+            }
+            g.cta_lo = cta;
+            g.ncta = ncta_tab[g.ncta_base + rank];
+            cta += g.ncta;
+        }
+    }
+    const int grid = static_cast<int>(segs.size());
+    if (grid > ctx->sm_count || grid == 0) return kPersistNotApplicable;
+
+    // ---- trees (D^2 sampling) ------------------------------------------------------------------------------
     std::vector<int> leaf_off_all, level_off_all, cfull_off(P, 0);
     std::vector<unsigned int> sched_all;
-    int cfull_total = 0, k_max = 1;
+    int cfull_total = 0, k_max = 1, lc_max = 1;
     int leaf_bound[ALQ_MAX_WORLD + 1] = {};
-    for (int p = 0; p < P; ++p) {
+    for (int p = 0; p < P && sample; ++p) {
         PGroup& g = groups[p];
-        g = PGroup{};
-        g.row_lo = comm ? 0 : D->part_off_host[p];
-        g.budget = D->budget_host[p];
-        g.pick_off = pick_off[p];
-        g.first_pick = D->first_pick_host ? D->first_pick_host[p] : -1;
-        g.n_leaves = 1;
-        if (!sample) continue;
         g.full_n = D->full_n_host[p];
         g.cfull_off = cfull_total;
         cfull_off[p] = cfull_total;
@@ -682,6 +844,7 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         // internal nodes in level order; node id = K + position in that order
         int hmax = 0;
         for (auto& nd : tb.internal) hmax = std::max(hmax, nd.height);
+        if (hmax > 38) return kPersistNotApplicable;
         std::vector<int> order, newid(tb.internal.size());
         g.level_base = static_cast<int>(level_off_all.size());
         for (int h = 1; h <= hmax; ++h) {
@@ -712,6 +875,11 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
             g.leaf_lo = leaf_bound[rank];
             g.leaf_hi = leaf_bound[rank + 1];
         }
+        if (g.ncta > 0) {
+            const int lc = (g.leaf_hi - g.leaf_lo + g.ncta - 1) / g.ncta;
+            if (lc > kGroups) return kPersistNotApplicable;       // one leaf per 8-lane group
+            lc_max = std::max(lc_max, lc);
+        }
     }
 
     // ---- shared-memory plan: centre + ring + tree ---------------------------------------------------------
@@ -719,7 +887,7 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     size_t smem = 0;
     {
         const size_t centre_bytes = static_cast<size_t>((d + c + 31) & ~31) * 4;
-        const size_t tree_bytes = sample ? static_cast<size_t>(k_max) * 12 + 64 : 64;
+        const size_t tree_bytes = sample ? static_cast<size_t>(k_max) * 12 + static_cast<size_t>(lc_max) * 512 + 64 : 64 + 12 + 512;
         const size_t fixed = centre_bytes + tree_bytes + kConsWarps * 16 + 256;
         const size_t budget_bytes = ctx->smem_optin > 8192 ? ctx->smem_optin - 1536 : 0;
         size_t tile_target = 32 * 1024;
@@ -739,54 +907,13 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         smem = centre_bytes + stages * tile_bytes + 2 * stages * sizeof(uint64_t) + kConsWarps * 16 + tree_bytes;
     }
 
-    // ---- CTAs: at most one per SM in total, split over the partitions by row count -------------------------
-    std::vector<BlockSeg> segs;
-    {
-        std::vector<int64_t> rows(P, 0);
-        int64_t total = 0;
-        for (int p = 0; p < P; ++p) {
-            if (D->budget_host[p] <= 0) continue;
-            rows[p] = comm ? (row_hi - row_lo) : (D->part_off_host[p + 1] - D->part_off_host[p]);
-            total += rows[p];
-        }
-        int left = ctx->sm_count - active;           // one CTA per active partition first, the rest by share
-        std::vector<int> nb(P, 0);
-        for (int p = 0; p < P; ++p) {
-            if (D->budget_host[p] <= 0) continue;
-            const int extra = total > 0 ? static_cast<int>(static_cast<int64_t>(ctx->sm_count - active) * rows[p] / total) : 0;
-            nb[p] = 1 + std::min(extra, left);
-            left -= nb[p] - 1;
-        }
-        for (int p = 0; p < P && left > 0; ++p)
-            if (nb[p] > 0 && rows[p] > nb[p]) { ++nb[p]; --left; }
-        int cta = 0;
-        for (int p = 0; p < P; ++p) {
-            if (nb[p] == 0) continue;
-            const int lo = comm ? row_lo : D->part_off_host[p];
-            const int64_t r = rows[p];
-            nb[p] = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nb[p], std::max<int64_t>(r, 1))));
-            groups[p].cta_lo = cta;
-            groups[p].ncta = nb[p];
-            for (int b = 0; b < nb[p]; ++b) {
-                BlockSeg s;
-                s.row_lo = lo + static_cast<int>(r * b / nb[p]);
-                s.row_hi = lo + static_cast<int>(r * (b + 1) / nb[p]);
-                s.part = p;
-                s.pad = 0;
-                segs.push_back(s);
-                ++cta;
-            }
-        }
-    }
-    const int grid = static_cast<int>(segs.size());
-    if (grid > ctx->sm_count) return kPersistNotApplicable;
-
     // ---- LL regions: identical layout in every window ------------------------------------------------------
     auto up = [](size_t v) { return (v + 127) & ~size_t(127); };
     size_t woff = up(8 * ALQ_MAX_WORLD);        // u64 ready[world] at offset 0
     for (int p = 0; p < P; ++p) {
         PGroup& g = groups[p];
-        g.keyw = static_cast<unsigned int>(woff);  woff = up(woff + static_cast<size_t>(2) * world * 16);
+        if (g.ncta == 0) continue;
+        g.keyw = static_cast<unsigned int>(woff);  woff = up(woff + static_cast<size_t>(2) * world * g.seg_stride * 8);
         g.pickw = static_cast<unsigned int>(woff); woff = up(woff + 2 * 8);
         if (sample) {
             g.leafw = static_cast<unsigned int>(woff); woff = up(woff + static_cast<size_t>(2) * g.n_leaves * 8);
@@ -799,12 +926,11 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
 
     // ---- scratch ----------------------------------------------------------------------------------------------
     const int total_picks = pick_off[P];
-    const size_t n_slots = static_cast<size_t>(P) * bmax;
     const size_t need = scratch_need({segs.size() * sizeof(BlockSeg), groups.size() * sizeof(PGroup),
                                       leaf_off_all.size() * 4 + 4, level_off_all.size() * 4 + 4, sched_all.size() * 4 + 4,
-                                      static_cast<size_t>(cfull_total) * 4 + 16, static_cast<size_t>(cfull_total) * 4 + 16,
-                                      static_cast<size_t>(total_picks) * 8 + 8, n_slots * 8, n_slots * 4, static_cast<size_t>(P) * 4,
-                                      static_cast<size_t>(P + 1) * 4, static_cast<size_t>(P) * 4, 64, 64, comm ? 0 : win_bytes});
+                                      static_cast<size_t>(cfull_total) * 8 + 16, static_cast<size_t>(cfull_total) * 4 + 16,
+                                      static_cast<size_t>(total_picks) * 8 + 8, segtab.size() * 4 + 4, ncta_tab.size() * 4 + 4,
+                                      static_cast<size_t>(P + 1) * 4, static_cast<size_t>(P) * 4, 64, 64 + 64 * static_cast<size_t>(grid), comm ? 0 : win_bytes});
     int rc = alq_scratch_reserve(ctx, need);
     if (rc) return rc;
     ScratchCursor cur(ctx->scratch);
@@ -813,25 +939,23 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     int* d_leaf_off = cur.take<int>(leaf_off_all.size() + 1);
     int* d_level_off = cur.take<int>(level_off_all.size() + 1);
     unsigned int* d_sched = cur.take<unsigned int>(sched_all.size() + 1);
-    float* d_cfull = cur.take<float>(cfull_total + 4);
+    unsigned long long* d_valw = cur.take<unsigned long long>(cfull_total + 2);
     int* d_posinv = cur.take<int>(cfull_total + 4);
     double* d_unif = cur.take<double>(total_picks + 1);
-    unsigned long long* d_best = cur.take<unsigned long long>(n_slots);
-    unsigned int* d_ticket = cur.take<unsigned int>(n_slots);
-    unsigned int* d_bar = cur.take<unsigned int>(P);
+    int* d_segtab = cur.take<int>(segtab.size() + 1);
+    int* d_ncta = cur.take<int>(ncta_tab.size() + 1);
     int* d_part_off = cur.take<int>(P + 1);
     int* d_cfull_off = cur.take<int>(P);
     int* d_status = cur.take<int>(1);
-    unsigned long long* d_prof = cur.take<unsigned long long>(4);
+    unsigned long long* d_prof = cur.take<unsigned long long>(8 + 8 * static_cast<size_t>(grid));
     char* d_win = comm ? Gc.window : cur.take<char>(win_bytes);
 
     ALQ_CUDA(ctx, cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(BlockSeg), cudaMemcpyHostToDevice, st));
     ALQ_CUDA(ctx, cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(PGroup), cudaMemcpyHostToDevice, st));
+    ALQ_CUDA(ctx, cudaMemcpyAsync(d_segtab, segtab.data(), segtab.size() * 4, cudaMemcpyHostToDevice, st));
+    ALQ_CUDA(ctx, cudaMemcpyAsync(d_ncta, ncta_tab.data(), ncta_tab.size() * 4, cudaMemcpyHostToDevice, st));
     ALQ_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(int), st));
-    ALQ_CUDA(ctx, cudaMemsetAsync(d_prof, 0, 4 * sizeof(unsigned long long), st));
-    ALQ_CUDA(ctx, cudaMemsetAsync(d_best, 0, n_slots * 8, st));
-    ALQ_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, n_slots * 4, st));
-    ALQ_CUDA(ctx, cudaMemsetAsync(d_bar, 0, static_cast<size_t>(P) * 4, st));
+    ALQ_CUDA(ctx, cudaMemsetAsync(d_prof, 0, (8 + 8 * static_cast<size_t>(grid)) * sizeof(unsigned long long), st));
     // LL regions start without any valid tag (after the ready[] words; peers only write them after our ready flag)
     ALQ_CUDA(ctx, cudaMemsetAsync(d_win + up(8 * ALQ_MAX_WORLD), 0, win_bytes - up(8 * ALQ_MAX_WORLD), st));
     if (sample) {
@@ -842,8 +966,7 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         ALQ_CUDA(ctx, cudaMemcpyAsync(d_unif, D->uniforms_host, static_cast<size_t>(total_picks) * 8, cudaMemcpyHostToDevice, st));
         ALQ_CUDA(ctx, cudaMemcpyAsync(d_part_off, D->part_off_host, static_cast<size_t>(P + 1) * 4, cudaMemcpyHostToDevice, st));
         ALQ_CUDA(ctx, cudaMemcpyAsync(d_cfull_off, cfull_off.data(), static_cast<size_t>(P) * 4, cudaMemcpyHostToDevice, st));
-        persist_fill_kernel<<<(cfull_total + 4 + 255) / 256, 256, 0, st>>>(d_cfull, cfull_total + 4, -INFINITY);
-        ALQ_LAUNCH_CHECK(ctx);
+        ALQ_CUDA(ctx, cudaMemsetAsync(d_valw, 0, static_cast<size_t>(cfull_total + 2) * 8, st));
         ALQ_CUDA(ctx, cudaMemsetAsync(d_posinv, 0xff, static_cast<size_t>(cfull_total + 4) * 4, st));
         persist_posinv_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(D->vpos, d_part_off, d_cfull_off, P, static_cast<int>(n), d_posinv);
         ALQ_LAUNCH_CHECK(ctx);
@@ -855,12 +978,11 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     A.xn = D->xn; A.an = D->an;
     A.mind = D->mind; A.vpos = D->vpos;
     A.segs = d_segs; A.groups = d_groups;
-    A.cfull = d_cfull; A.posinv = d_posinv;
+    A.valw = d_valw; A.posinv = d_posinv;
     A.leaf_off = d_leaf_off; A.level_off = d_level_off; A.sched = d_sched; A.uniforms = d_unif;
-    A.best = d_best; A.ticket = d_ticket; A.bar = d_bar;
+    A.segtab = d_segtab; A.ncta_of_rank = d_ncta;
     A.picks = D->picks; A.status = d_status;
     A.prof = D->step_kernel_ms_host ? d_prof : nullptr;
-    A.bmax = bmax;
     A.world = world; A.rank = rank;
     for (int r = 0; r < ALQ_MAX_WORLD; ++r) A.peer[r] = nullptr;
     if (comm) for (int r = 0; r < world; ++r) A.peer[r] = Gc.peer[r];
@@ -879,8 +1001,8 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         ALQ_LAUNCH_CHECK(ctx);
     }
     cudaError_t le;
-    if (factored) le = sample ? launch_persist<true, true>(grid, smem, st, A, cfg, k_max) : launch_persist<true, false>(grid, smem, st, A, cfg, k_max);
-    else le = sample ? launch_persist<false, true>(grid, smem, st, A, cfg, k_max) : launch_persist<false, false>(grid, smem, st, A, cfg, k_max);
+    if (factored) le = sample ? launch_persist<true, true>(grid, smem, st, A, cfg, k_max, lc_max) : launch_persist<true, false>(grid, smem, st, A, cfg, k_max, lc_max);
+    else le = sample ? launch_persist<false, true>(grid, smem, st, A, cfg, k_max, lc_max) : launch_persist<false, false>(grid, smem, st, A, cfg, k_max, lc_max);
     if (le != cudaSuccess) {
         cudaGetLastError();
         ALQ_FAIL(ctx, ALQ_ERR_CUDA, "alq_greedy_select: cooperative launch failed: %s (grid %d, %zu B shared)", cudaGetErrorString(le), grid, smem);
@@ -888,7 +1010,7 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     ALQ_LAUNCH_CHECK(ctx);
 
     int status = 0;
-    unsigned long long prof[4] = {};
+    unsigned long long prof[8] = {};
     if (sample || comm || D->step_kernel_ms_host) {
         ALQ_CUDA(ctx, cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (D->step_kernel_ms_host) ALQ_CUDA(ctx, cudaMemcpyAsync(prof, d_prof, sizeof(prof), cudaMemcpyDeviceToHost, st));
@@ -900,6 +1022,25 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         D->step_kernel_ms_host[1] = static_cast<float>(prof[1] * 1e-6 / steps);
         D->step_kernel_ms_host[2] = static_cast<float>(prof[2]);
         D->step_kernel_ms_host[3] = 3.0f;
+        for (int i = 0; i < 4; ++i) D->step_kernel_ms_host[4 + i] = static_cast<float>(prof[3 + i] * 1e-6 / steps);
+    }
+    if (D->step_kernel_ms_host && getenv("ALQ_PERSIST_DEBUG")) {      // per-CTA stamps of the middle step: where does the grid wait?
+        std::vector<unsigned long long> h(8 * static_cast<size_t>(grid));
+        cudaMemcpy(h.data(), d_prof + 8, h.size() * 8, cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int b = 0; b < grid; ++b) if (h[8 * b] && h[8 * b] < t0) t0 = h[8 * b];
+        static const char* names[8] = {"stream end", "values known", "S known", "mass stored", "masses polled", "leaf located", "search done (owner)", "pick known"};
+        for (int k = 0; k < 8; ++k) {
+            unsigned long long mn = ~0ull, mx = 0;
+            double mean = 0;
+            int cnt = 0;
+            for (int b = 0; b < grid; ++b) {
+                if (!h[8 * b + k]) continue;
+                const unsigned long long v = h[8 * b + k] - t0;
+                mn = std::min(mn, v); mx = std::max(mx, v); mean += v; ++cnt;
+            }
+            if (cnt) fprintf(stderr, "[alq persist dbg] %-20s min %7.2f mean %7.2f max %7.2f us (%d CTAs) after the first CTA's stream end\n", names[k], mn * 1e-3, mean / cnt * 1e-3, mx * 1e-3, cnt);
+        }
     }
     if (status == ALQ_ERR_STATE) ALQ_FAIL(ctx, status, "alq_greedy_select: timed out waiting for a peer GPU (or a CTA of this grid)");
     if (status != 0) ALQ_FAIL(ctx, status, "alq_greedy_select: non-finite or empty probability mass during D^2 sampling");

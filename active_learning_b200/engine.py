@@ -338,7 +338,7 @@ class Engine:
                 keep.append(sp)
         desc.picks = picks.data_ptr()
         desc.variant = int(variant)
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 8)()
         if time_steps:
             desc.step_kernel_ms_host = C.addressof(ms)
         self._check(self.lib.alq_greedy_select(self._h, C.byref(desc), self._stream()), "alq_greedy_select")
@@ -346,6 +346,7 @@ class Engine:
         del keep
         if time_steps:
             self.last_greedy_timing = {"stream_ms": float(ms[0]), "select_ms": float(ms[1]), "steps": int(ms[2]),
-                                       "variant": int(ms[3])}
+                                       "variant": int(ms[3]),
+                                       "select_phases_ms": [float(ms[i]) for i in range(4, 8)]}
             return out, float(ms[0])
         return out

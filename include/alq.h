@@ -197,10 +197,11 @@ typedef struct alq_greedy_desc {
        windows (leaf sums, leaf masses, the pick): one-way NVLink stores, no fences, no collective library. */
     const int32_t* shard_off_host;
     const int32_t* shard_pos_host;
-    /* optional timing out-parameter (forces a stream synchronisation at the end of the call), 4 floats in ms:
+    /* optional timing out-parameter (forces a stream synchronisation at the end of the call), 8 floats in ms:
        [0] mean time of the streaming phase of a step (variants 1/2: CUDA events around the step kernel; variant 3:
        %globaltimer stamps taken by CTA 0), [1] mean time of the selection phase (barrier + exchange + draw) of a step
-       (variant 3 only), [2] steps measured, [3] the variant that ran. */
+       (variant 3 only), [2] steps measured, [3] the variant that ran, [4..7] variant 3, D^2 draw: mean time CTA 0 spends
+       waiting for its leaf's values / leaf sums + tree fold / leaf masses + scan / in-leaf search + pick. */
     float* step_kernel_ms_host;
 } alq_greedy_desc;
 

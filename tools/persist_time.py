@@ -50,5 +50,6 @@ for fac in (False, True):
                           "loop_us_per_step": round(loop_us, 2), "loop_frac": round(N * row_bytes / loop_us / 1e3 / PEAK, 4),
                           "stream_us": round(tm["stream_ms"] * 1e3, 2), "select_us": round(tm["select_ms"] * 1e3, 2),
                           "stream_frac": round(N * row_bytes / max(tm["stream_ms"], 1e-9) / 1e6 / PEAK, 4),
+                          "select_phases_us": [round(v * 1e3, 2) for v in tm["select_phases_ms"]],
                           "picks_equal_first_variant": bool(np.array_equal(ref, picks)),
                           "tile_kb": os.environ.get("ALQ_TILE_KB"), "max_stages": os.environ.get("ALQ_MAX_STAGES")}), flush=True)

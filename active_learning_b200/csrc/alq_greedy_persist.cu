@@ -28,7 +28,7 @@
 namespace {
 
 constexpr int kMaxLeaves = 4096;          // per partition: 2*K floats + K words of shared memory
-constexpr int kConsWarps = 15;          // + 1 producer warp = 16 warps = 4 per SM sub-partition: 128 registers per thread
+constexpr int kConsWarps = 11;          // + 1 producer warp = 12 warps = 3 per SM sub-partition: up to 168 registers per thread, no spills
 constexpr int kConsThreads = kConsWarps * 32;
 constexpr int kGroups = kConsThreads / 8; // 8-lane groups per CTA == leaves a CTA can own
 
@@ -44,7 +44,7 @@ struct PGroup {                 // one partition = one group of CTAs
     int leaf_lo, leaf_hi;       // leaves summed by THIS rank
     int seg_base, seg_stride;   // segtab[seg_base + r * seg_stride + cta] = first row of CTA `cta` of rank r
     int ncta_base;              // ncta_of_rank[ncta_base + r] = CTAs rank r runs for this partition
-    unsigned int keyw, leafw, massw, pickw;   // byte offsets of the LL regions inside a window
+    unsigned int keyw, leafw, massw, pickw, umw;   // byte offsets of the LL regions inside a window
 };
 
 struct PersistArgs {
@@ -72,6 +72,7 @@ struct PersistArgs {
     unsigned int ready_off;        // u64 ready[world] at the head of every window
     unsigned long long ready_tag;
     unsigned int tag_base;         // 0x80000000 | (epoch & 0x7f) << 24
+    int fast_path;                 // D^2 draw: certified per-CTA-mass path first (0: always the exact NumPy-tree machinery)
     long long timeout_cycles;
 };
 
@@ -181,9 +182,282 @@ __device__ __forceinline__ float leaf_sum_regs(const float (&v)[16], int len, in
     return __shfl_sync(gmask, r, g0);
 }
 
+// First item i of [0, n) with mass(i) > 0 and (base0 + mass(0) + .. + mass(i)) / total > u_hi, found by the whole
+// consumer block: idx (-1: none), base = the prefix before that item (base0 included), sum = mass(0) + .. + mass(n-1).
+// One fixed association (thread chunks -> lanes -> warps): every CTA of every rank that runs it on the same masses
+// gets the same answer.  total_in < 0: use the sum itself as the total.
+template <typename Mass>
+__device__ __forceinline__ void block_locate(int n, int ct, int cw, int lane, double u_hi, double base0, double total_in,
+                                             Mass mass, double* sh_w, int* sh_hw, double* sh_bw, int& idx, double& base, double& sum) {
+    const int per = (n + kConsThreads - 1) / kConsThreads;
+    const int i0 = min(n, ct * per), i1 = min(n, i0 + per);
+    double loc = 0.0;
+    for (int i = i0; i < i1; ++i) loc += mass(i);
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double w = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += w;
+    }
+    if (lane == 31) sh_w[cw] = inc;
+    const double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    cons_bar();
+    double woff = 0.0, tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kConsWarps; ++w) {
+        if (w == cw) woff = tot;
+        tot += sh_w[w];
+    }
+    sum = tot;
+    const double total = total_in < 0.0 ? tot : total_in;
+    double run = base0 + woff + (lane ? prev : 0.0);
+    int hit = -1;
+    double hb = 0.0;
+    for (int i = i0; i < i1; ++i) {
+        const double before = run, m = mass(i);
+        run += m;
+        if (hit < 0 && m > 0.0 && (run / total) > u_hi) { hit = i; hb = before; }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit >= 0);
+    const int src = bal ? __ffs(bal) - 1 : 0;
+    const int wh = __shfl_sync(0xffffffffu, hit, src);
+    const double wb = __shfl_sync(0xffffffffu, hb, src);
+    if (lane == 0) { sh_hw[cw] = bal ? wh : -1; sh_bw[cw] = wb; }
+    cons_bar();
+    idx = -1;
+    base = 0.0;
+#pragma unroll
+    for (int w = 0; w < kConsWarps; ++w)
+        if (idx < 0 && sh_hw[w] >= 0) { idx = sh_hw[w]; base = sh_bw[w]; }
+    cons_bar();                               // sh_* are reused by the next call
+}
+
+// The exact D^2 draw, NumPy operation for operation (coreset_sampler.py:84-92): leaf sums of the float32 pairwise
+// tree -> S -> fp64 mass of fl32(c / S) per leaf -> the leaf and the element where cumsum / total crosses u.  Taken when
+// the certified fast path cannot decide (and always with d2_fast_path = 0); out of line so that its registers (16
+// values per lane live across three exchanges) do not weigh on the streaming loop.
+struct SelShared {
+    double w[kConsWarps];
+    double bw[kConsWarps];
+    double base, base_nz;
+    int hw[kConsWarps];
+    int level[40];
+    int centre, hit, nz;
+    unsigned long long prof[10];   // CTA 0 / thread 0 only: [0] stream [1] select [2..5] phases [6] step start [7] last stamp [8] stream end
+};
+
+__device__ __noinline__ int exact_draw(const PersistArgs& A, const PGroup* Gp, SelShared* ss, float* val, const unsigned int* s_sched,
+                                       const int* s_rows, int grank, unsigned int vtag, double u, unsigned int* rnd,
+                                       int my_leaf, int leaf_pos, int leaf_len, unsigned int cand_mask) {
+    const PGroup G = *Gp;                     // a private copy: the caller's stays in registers
+    const int ct = threadIdx.x - 32, cw = ct >> 5, lane = ct & 31;
+    const int grp = ct >> 3, g_lane = ct & 7;
+    const unsigned gmask = 0xffu << ((lane >> 3) * 8);
+    char* const win = A.peer[A.rank];
+    const int K = G.n_leaves;
+    const int root = K > 1 ? 2 * K - 2 : 0;
+    unsigned long long* const valw = A.valw + G.cfull_off;
+    unsigned int& rnd_leaf = rnd[0];
+    unsigned int& rnd_mass = rnd[1];
+    unsigned int& rnd_pick = rnd[2];
+    int centre = G.row_lo;
+    // ---- (1) this group's leaf: wait for this step's min-distance of every candidate position ----
+    float v[16];
+    {
+        // all loads of a round are issued before any tag is looked at: one L2 round trip per round, not 16
+        unsigned int pend = cand_mask;
+        const unsigned long long* base = valw + leaf_pos + g_lane;
+        const long long t0 = clock64();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = ALQ_NEG_INF;          // labeled / padding positions: prob 0
+        if (pend) {                   // one word per lane until it is there: no flood while the rows still stream
+            const unsigned long long* sp = base + 8 * (31 - __clz(pend));
+            for (int spin = 0; static_cast<unsigned int>(ll_load(sp) >> 32) != vtag; ++spin) {
+                if (ll_give_up(spin, t0, A)) break;
+                __nanosleep(40);
+            }
+        }
+        for (int spin = 0; pend; ++spin) {
+            unsigned long long w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (pend & (1u << j)) w[j] = ll_load(base + 8 * j);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if ((pend & (1u << j)) && static_cast<unsigned int>(w[j] >> 32) == vtag) {
+                    v[j] = __uint_as_float(static_cast<unsigned int>(w[j]));
+                    pend &= ~(1u << j);
+                }
+            if (pend && ll_give_up(spin, t0, A)) break;
+        }
+    }
+    float total32 = 0.f;
+    bool failed = false;
+    for (int attempt = 0;; ++attempt) {
+        // ---- (2) leaf sums of NumPy's pairwise tree -> every rank; fold the tree in shared memory ----
+        const unsigned int tag = A.tag_base | (++rnd_leaf & 0xffffffu);
+        const unsigned int slot = rnd_leaf & 1u;
+        if (my_leaf >= 0) {
+            const float s = leaf_sum_regs(v, leaf_len, lane, gmask);
+            if (g_lane < A.world)
+                ll_store(A.peer[g_lane] + G.leafw + (static_cast<size_t>(slot) * K + my_leaf) * 8, tag, __float_as_uint(s));
+        }
+        ll_gather(win + G.leafw + static_cast<size_t>(slot) * K * 8, K, 8, tag, 32, A, ct,
+                  [&](int i, unsigned long long w) { val[i] = __uint_as_float(static_cast<unsigned int>(w)); });
+        cons_bar();
+        {
+            int h = 0;
+            for (; h < G.n_levels && ss->level[h + 1] - ss->level[h] > 32; ++h) {     // wide levels: the whole block
+                const int lo = ss->level[h], hi = ss->level[h + 1];
+                for (int j = lo + ct; j < hi; j += kConsThreads) {
+                    const unsigned int e = s_sched[j];
+                    val[K + j] = val[e & 0xffffu] + val[e >> 16];
+                }
+                cons_bar();
+            }
+            if (cw == 0)                                                          // the top of the tree: one warp
+                for (; h < G.n_levels; ++h) {
+                    const int lo = ss->level[h], hi = ss->level[h + 1];
+                    for (int j = lo + lane; j < hi; j += 32) {
+                        const unsigned int e = s_sched[j];
+                        val[K + j] = val[e & 0xffffu] + val[e >> 16];
+                    }
+                    __syncwarp();
+                }
+        }
+        cons_bar();
+        total32 = val[root];
+        cons_bar();                                   // val is reused below
+        if (total32 > 0.f && total32 <= 3.4028234e38f) break;
+        if (!(total32 == 0.f) || attempt > (1 << 20)) { failed = true; break; }   // NaN / inf mass
+        // sum == 0 -> prob is NaN -> `min_dist_labeled += 0.00001` and retry (:87-90): on the register copy of
+        // this step's values, so the bump never outlives this draw (the next step brings fresh values)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += 0.00001f;
+    }
+    if (failed) {                                     // the same decision in every CTA of every rank
+        if (ct == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
+        centre = G.row_lo;
+    } else {
+        // ---- (3) fp64 mass of prob = clip(mind, 0) / S per leaf -> every rank ----
+        const unsigned int tag = A.tag_base | (++rnd_mass & 0xffffffu);
+        const unsigned int slot = rnd_mass & 1u;
+        if (my_leaf >= 0) {
+            double m = 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m += prob64(v[j], total32);
+            m += __shfl_down_sync(gmask, m, 1, 8);
+            m += __shfl_down_sync(gmask, m, 2, 8);
+            m += __shfl_down_sync(gmask, m, 4, 8);
+            m = __shfl_sync(gmask, m, lane & ~7);
+            if (g_lane < A.world) {
+                char* dst = A.peer[g_lane] + G.massw + (static_cast<size_t>(slot) * K + my_leaf) * 16;
+                ll_store(dst, tag, static_cast<unsigned int>(__double2hiint(m)));
+                ll_store(dst + 8, tag, static_cast<unsigned int>(__double2loint(m)));
+            }
+        }
+        double* M = reinterpret_cast<double*>(val);   // K doubles == 2K floats
+        {
+            unsigned int* M32 = reinterpret_cast<unsigned int*>(M);      // word 2i = hi, 2i + 1 = lo of leaf i
+            ll_gather(win + G.massw + static_cast<size_t>(slot) * K * 16, 2 * K, 8, tag, 32, A, ct,
+                      [&](int i, unsigned long long w) { M32[i ^ 1] = static_cast<unsigned int>(w); });   // little endian: lo first
+        }
+        if (ct == 0) { ss->hit = 0x7fffffff; ss->nz = -1; }
+        cons_bar();
+        // ---- np.random.choice == first k with cumsum64(p)[k] / total > u: locate the leaf.  One fixed
+        //      chain (thread chunks -> lanes -> warps), identical in every CTA of every rank. ----
+        const int per = (K + kConsThreads - 1) / kConsThreads;
+        const int l0 = min(K, ct * per), l1 = min(K, l0 + per);
+        double loc = 0.0;
+        for (int l = l0; l < l1; ++l) loc += M[l];
+        double inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double w = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += w;
+        }
+        if (lane == 31) ss->w[cw] = inc;
+        const double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+        cons_bar();
+        double woff = 0.0, total = 0.0;
+        for (int w = 0; w < kConsWarps; ++w) {
+            if (w == cw) woff = total;
+            total += ss->w[w];
+        }
+        double run = woff + (lane ? prev : 0.0);
+        int my_hit = 0x7fffffff, my_nz = -1;
+        double hit_base = 0.0, nz_base = 0.0;
+        for (int l = l0; l < l1; ++l) {
+            const double before = run;
+            run += M[l];
+            if (M[l] > 0.0) { my_nz = l; nz_base = before; }
+            if (my_hit == 0x7fffffff && (run / total) > u) { my_hit = l; hit_base = before; }
+        }
+        {
+            const int wh = __reduce_min_sync(0xffffffffu, my_hit), wn = __reduce_max_sync(0xffffffffu, my_nz);
+            if (lane == 0) {
+                if (wh != 0x7fffffff) atomicMin(&ss->hit, wh);
+                if (wn >= 0) atomicMax(&ss->nz, wn);
+            }
+        }
+        cons_bar();
+        if (my_hit != 0x7fffffff && my_hit == ss->hit) ss->base = hit_base;
+        if (my_nz >= 0 && my_nz == ss->nz) ss->base_nz = nz_base;
+        cons_bar();
+        int leaf = ss->hit;
+        double base = ss->base;
+        if (leaf == 0x7fffffff) { leaf = ss->nz; base = ss->base_nz; }   // u beyond the last mass by an ulp
+        // ---- (4) the group that owns the leaf searches inside it (values still in registers) ----
+        const unsigned int ptag = A.tag_base | (++rnd_pick & 0xffffffu);
+        const unsigned int pslot = rnd_pick & 1u;
+        if (leaf < 0 && grank == 0 && A.rank == 0 && cw == 0) {       // no mass at all: cannot happen with S > 0
+            if (lane == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
+            if (lane < A.world) ll_store(A.peer[lane] + G.pickw + pslot * 8, ptag, static_cast<unsigned int>(G.row_lo));
+        }
+        if (leaf >= 0 && leaf == my_leaf) {           // whole 8-lane group, uniformly
+            // sequential order k = 8j + lane: scan 8 lanes per j, carry across j
+            double carry = base;
+            int hit = -1, nz = -1;
+            const int g0 = lane & ~7;
+            for (int j = 0; j < 16 && 8 * j < leaf_len; ++j) {
+                double pj = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj)
+                    if (jj == j) pj = prob64(v[jj], total32);
+                double sc = pj;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const double w = __shfl_up_sync(gmask, sc, o, 8);
+                    if (g_lane >= o) sc += w;
+                }
+                const double rk = carry + sc;
+                const bool cross = pj > 0.0 ? ((rk / total) > u) : false;
+                // an element with zero mass can cross only if an earlier one did: ignore it
+                const unsigned cb = (__ballot_sync(gmask, cross) >> g0) & 0xffu;
+                const unsigned zb = (__ballot_sync(gmask, pj > 0.0) >> g0) & 0xffu;
+                if (zb) nz = 8 * j + (31 - __clz(zb));
+                if (cb) { hit = 8 * j + (__ffs(cb) - 1); break; }
+                carry = __shfl_sync(gmask, rk, g0 + 7);
+            }
+            const int k = hit >= 0 ? hit : nz;        // no crossing: re-association moved it by an ulp
+            int row = k >= 0 ? s_rows[grp * 128 + k] : -1;
+            if (row < 0) {
+                if (g_lane == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
+                row = G.row_lo;
+            }
+            if (g_lane < A.world) ll_store(A.peer[g_lane] + G.pickw + pslot * 8, ptag, static_cast<unsigned int>(row));
+        }
+        if (ct == 0) ss->centre = static_cast<int>(ll_wait(win + G.pickw + pslot * 8, ptag, A));
+        cons_bar();
+        centre = ss->centre;
+    }
+
+    return centre;
+}
+
 template <bool FACTORED, bool SAMPLE>
 __global__ void __launch_bounds__(32 * (1 + kConsWarps), 1)
-greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, const int lc_max) {
+greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, const int k_max, const int lc_max, const int ne_max) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int d = A.d, c = FACTORED ? A.c : 0;
     const int dv = d >> 2, cv = c >> 2;
@@ -192,14 +466,11 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, c
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(cfg.stages) * cfg.tile_floats);
     uint64_t* empty = full + cfg.stages;
     unsigned long long* sbest = reinterpret_cast<unsigned long long*>(empty + cfg.stages);   // [kConsWarps]
-    double* sh_w = reinterpret_cast<double*>(sbest + kConsWarps);                             // [kConsWarps]
-    float* val = reinterpret_cast<float*>(sh_w + kConsWarps);                                 // [2 * k_max] (SAMPLE)
+    float* val = reinterpret_cast<float*>(sbest + kConsWarps + 1);                                 // [2 * k_max] (SAMPLE)
     unsigned int* s_sched = reinterpret_cast<unsigned int*>(val + 2 * static_cast<size_t>(k_max));   // [k_max]
     int* s_rows = reinterpret_cast<int*>(s_sched + k_max);                                    // [lc_max * 128] row of each owned position
-    __shared__ int s_level[40];
-    __shared__ int sh_centre, sh_hit, sh_nz;
-    __shared__ double sh_base, sh_base_nz;
-    __shared__ unsigned long long s_prof[10];  // CTA 0 / thread 0 only: [0] stream [1] select [2..5] phases [6] step start [7] last stamp [8] stream end
+    double* s_u = reinterpret_cast<double*>(s_rows + static_cast<size_t>(lc_max) * 128);        // [ne_max] per-CTA masses of every rank (SAMPLE)
+    __shared__ SelShared ss;
 
     const BlockSeg seg = A.segs[blockIdx.x];
     const PGroup G = A.groups[seg.part];
@@ -219,7 +490,7 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, c
     }
     if (SAMPLE) {
         for (int i = threadIdx.x; i < G.n_leaves - 1; i += blockDim.x) s_sched[i] = A.sched[G.sched_base + i];
-        if (threadIdx.x <= G.n_levels && threadIdx.x < 40) s_level[threadIdx.x] = A.level_off[G.level_base + threadIdx.x];
+        if (threadIdx.x <= G.n_levels && threadIdx.x < 40) ss.level[threadIdx.x] = A.level_off[G.level_base + threadIdx.x];
     }
     __syncthreads();
 
@@ -308,19 +579,20 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, c
     unsigned int my_par = 0;
     for (int q = cw / cfg.stages; q > 0; --q) my_par ^= 1u;
 
-    unsigned int rnd_key = 0, rnd_leaf = 0, rnd_mass = 0, rnd_pick = 0;
+    unsigned int rnd_key = 0, rnd_leaf = 0, rnd_mass = 0, rnd_pick = 0, rnd_u = 0;
     int centre = -1;
     const bool prof = A.prof != nullptr && blockIdx.x == 0 && ct == 0;
-    if (prof) for (int i = 0; i < 10; ++i) s_prof[i] = 0;
+    if (prof) { for (int i = 0; i < 10; ++i) ss.prof[i] = 0; ss.prof[9] = gtime_ns(); }
     const int dbg_step = G.budget / 2;
     unsigned long long* const dbg = (A.prof != nullptr && ct == 0) ? A.prof + 8 + 8 * blockIdx.x : nullptr;   // per-CTA stamps of one step
 
     for (int t = 0; t < G.budget; ++t) {
         unsigned long long best_key = 0ull;   // arg-max: ord(min-distance) << 32 | ~(row - seg.row_lo)
+        double usum = 0.0;                    // D^2: fp64 mass clip(mind, 0) of the rows this lane finished
         const unsigned int vtag = A.tag_base | (static_cast<unsigned int>(t + 1) & 0xffffffu);
         double u = 0.0;
         if (SAMPLE) u = __ldg(A.uniforms + G.pick_off + t);           // needed late: issue the load now
-        if (prof) s_prof[6] = gtime_ns();
+        if (prof) ss.prof[6] = gtime_ns();
         if (t == 0) {
             if (G.first_pick >= 0) {          // centre 0 chosen by the caller: no selection
                 centre = G.first_pick;
@@ -329,8 +601,10 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, c
             }
             for (int row = seg.row_lo + ct; row < seg.row_hi; row += kConsThreads) {
                 const float m = __ldcg(A.mind + row);
-                if (SAMPLE) ll_store(valw + A.vpos[row], vtag, __float_as_uint(m));
-                else {
+                if (SAMPLE) {
+                    ll_store(valw + A.vpos[row], vtag, __float_as_uint(m));
+                    usum += static_cast<double>(fmaxf(m, 0.f));
+                } else {
                     const unsigned long long k = (static_cast<unsigned long long>(alq_ord(m)) << 32) | (0xffffffffu - static_cast<uint32_t>(row - seg.row_lo));
                     best_key = k > best_key ? k : best_key;
                 }
@@ -400,8 +674,10 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, c
                         float m = fminf(m_old, dist_dense(n_i, qn, my_d2));
                         if (row == centre) m = ALQ_NEG_INF;         // a picked row is never a candidate again
                         __stcg(A.mind + row, m);
-                        if (SAMPLE) ll_store(valw + vp, vtag, __float_as_uint(m));   // raw running min; the draw clips at 0
-                        else {
+                        if (SAMPLE) {
+                            ll_store(valw + vp, vtag, __float_as_uint(m));   // raw running min (exact path); the draw clips at 0
+                            usum += static_cast<double>(fmaxf(m, 0.f));
+                        } else {
                             const unsigned long long k = (static_cast<unsigned long long>(alq_ord(m)) << 32) | (0xffffffffu - static_cast<uint32_t>(row - seg.row_lo));
                             best_key = k > best_key ? k : best_key;
                         }
@@ -419,7 +695,7 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, c
             best_key = warp_max_u64(best_key);
             if (lane == 0) sbest[cw] = best_key;
             cons_bar();
-            if (prof) s_prof[8] = gtime_ns();
+            if (prof) ss.prof[8] = gtime_ns();
             if (dbg && t == dbg_step) dbg[0] = gtime_ns();
             const unsigned int tag16 = 0x8000u | ((A.tag_base >> 12) & 0x7000u) | (++rnd_key & 0xfffu);
             const unsigned int slot = rnd_key & 1u;
@@ -453,221 +729,98 @@ greedy_persist_kernel(const PersistArgs A, const PipeCfg cfg, const int k_max, c
             for (int w = 1; w < kConsWarps; ++w) kk = sbest[w] > kk ? sbest[w] : kk;
             centre = static_cast<int>(alq_maxkey_row(kk));
         } else {
-            if (prof) s_prof[8] = gtime_ns();
+            if (prof) ss.prof[8] = gtime_ns();
             if (dbg && t == dbg_step) dbg[0] = gtime_ns();
-            // ---- (1) this group's leaf: wait for this step's min-distance of every candidate position ----
-            float v[16];
-            {
-                // all loads of a round are issued before any tag is looked at: one L2 round trip per round, not 16
-                unsigned int pend = cand_mask;
-                const unsigned long long* base = valw + leaf_pos + g_lane;
-                const long long t0 = clock64();
+            // ================= certified fast path =================
+            // np.random.choice picks the first k with cdf[k] > u, cdf = cumsum64(fl32(c / S)) / its last entry.  Every
+            // fl32(c_i / S) is c_i / S (1 + e_i), |e_i| <= 2^-24 (or an absolute 2^-150 when it underflows), and S cancels
+            // in the ratio, so cdf[k] = Q[k] / Q[n-1] (1 + d), |d| <= 2^-23, with Q the plain fp64 prefix sums of
+            // c = clip(mind, 0).  If Q[k]/Q[n-1] > u + m and Q[k-1]/Q[n-1] <= u - m (m = 1.3e-7 > 2^-23 + fp64 noise) then k IS
+            // NumPy's pick -- no float32 pairwise tree, no per-leaf masses.  Q needs one exchange of one fp64 mass per
+            // CTA; the CTA holding the crossing searches its own rows.  A step whose u falls inside a margin (about 2 %
+            // of the steps at 80 000 rows), or whose mass is zero / non-finite, takes the exact machinery below.
+            bool exact = A.fast_path == 0;
+            if (!exact) {
+                constexpr double kMargin = 1.3e-7;
+                const int stride = G.seg_stride, ne = A.world * stride;
+                const unsigned int utag = A.tag_base | (++rnd_u & 0xffffffu);
+                const unsigned int uslot = rnd_u & 1u;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = ALQ_NEG_INF;          // labeled / padding positions: prob 0
-                if (pend) {                   // one word per lane until it is there: no flood while the rows still stream
-                    const unsigned long long* sp = base + 8 * (31 - __clz(pend));
-                    for (int spin = 0; static_cast<unsigned int>(ll_load(sp) >> 32) != vtag; ++spin) {
-                        if (ll_give_up(spin, t0, A)) break;
-                        __nanosleep(40);
-                    }
-                }
-                for (int spin = 0; pend; ++spin) {
-                    unsigned long long w[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (pend & (1u << j)) w[j] = ll_load(base + 8 * j);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if ((pend & (1u << j)) && static_cast<unsigned int>(w[j] >> 32) == vtag) {
-                            v[j] = __uint_as_float(static_cast<unsigned int>(w[j]));
-                            pend &= ~(1u << j);
-                        }
-                    if (pend && ll_give_up(spin, t0, A)) break;
-                }
-            }
-            if (prof) { const unsigned long long x0 = gtime_ns(); s_prof[2] += x0 - s_prof[8]; s_prof[7] = x0; }
-            if (dbg && t == dbg_step) dbg[1] = gtime_ns();
-            float total32 = 0.f;
-            bool failed = false;
-            for (int attempt = 0;; ++attempt) {
-                // ---- (2) leaf sums of NumPy's pairwise tree -> every rank; fold the tree in shared memory ----
-                const unsigned int tag = A.tag_base | (++rnd_leaf & 0xffffffu);
-                const unsigned int slot = rnd_leaf & 1u;
-                if (my_leaf >= 0) {
-                    const float s = leaf_sum_regs(v, leaf_len, lane, gmask);
-                    if (g_lane < A.world)
-                        ll_store(A.peer[g_lane] + G.leafw + (static_cast<size_t>(slot) * K + my_leaf) * 8, tag, __float_as_uint(s));
-                }
-                ll_gather(win + G.leafw + static_cast<size_t>(slot) * K * 8, K, 8, tag, 32, A, ct,
-                          [&](int i, unsigned long long w) { val[i] = __uint_as_float(static_cast<unsigned int>(w)); });
+                for (int o = 16; o > 0; o >>= 1) usum += __shfl_xor_sync(0xffffffffu, usum, o);
+                if (lane == 0) ss.w[cw] = usum;
                 cons_bar();
-                {
-                    int h = 0;
-                    for (; h < G.n_levels && s_level[h + 1] - s_level[h] > 32; ++h) {     // wide levels: the whole block
-                        const int lo = s_level[h], hi = s_level[h + 1];
-                        for (int j = lo + ct; j < hi; j += kConsThreads) {
-                            const unsigned int e = s_sched[j];
-                            val[K + j] = val[e & 0xffffu] + val[e >> 16];
-                        }
-                        cons_bar();
+                if (cw == 0) {
+                    double tot = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kConsWarps; ++w) tot += ss.w[w];
+                    const size_t off = G.umw + (static_cast<size_t>(uslot) * ne + static_cast<size_t>(A.rank) * stride + grank) * 16;
+                    if (lane < A.world) {
+                        ll_store(A.peer[lane] + off, utag, static_cast<unsigned int>(__double2hiint(tot)));
+                        ll_store(A.peer[lane] + off + 8, utag, static_cast<unsigned int>(__double2loint(tot)));
                     }
-                    if (cw == 0)                                                          // the top of the tree: one warp
-                        for (; h < G.n_levels; ++h) {
-                            const int lo = s_level[h], hi = s_level[h + 1];
-                            for (int j = lo + lane; j < hi; j += 32) {
-                                const unsigned int e = s_sched[j];
-                                val[K + j] = val[e & 0xffffu] + val[e >> 16];
+                    if (grank == 0)           // slots of this rank beyond its CTA count: zero mass
+                        for (int e = G.ncta + (lane >> 3); e < stride; e += 4)
+                            if ((lane & 7) < A.world) {
+                                char* q = A.peer[lane & 7] + G.umw + (static_cast<size_t>(uslot) * ne + static_cast<size_t>(A.rank) * stride + e) * 16;
+                                ll_store(q, utag, 0u);
+                                ll_store(q + 8, utag, 0u);
                             }
-                            __syncwarp();
-                        }
+                }
+                cons_bar();                   // ss.w is reused by block_locate
+                {
+                    unsigned int* u32 = reinterpret_cast<unsigned int*>(s_u);
+                    ll_gather(win + G.umw + static_cast<size_t>(uslot) * ne * 16, 2 * ne, 8, utag, 32, A, ct,
+                              [&](int i, unsigned long long w) { u32[i ^ 1] = static_cast<unsigned int>(w); });
                 }
                 cons_bar();
-                total32 = val[root];
-                cons_bar();                                   // val is reused below
-                if (total32 > 0.f && total32 <= 3.4028234e38f) break;
-                if (!(total32 == 0.f) || attempt > (1 << 20)) { failed = true; break; }   // NaN / inf mass
-                // sum == 0 -> prob is NaN -> `min_dist_labeled += 0.00001` and retry (:87-90): on the register copy of
-                // this step's values, so the bump never outlives this draw (the next step brings fresh values)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += 0.00001f;
+                if (dbg && t == dbg_step) dbg[1] = gtime_ns();
+                int e_hit;
+                double e_base, q_tot;
+                block_locate(ne, ct, cw, lane, u + kMargin, 0.0, -1.0, [&](int i) { return s_u[i]; }, ss.w, ss.hw, ss.bw, e_hit, e_base, q_tot);
+                const bool sane = q_tot > 0.0 && q_tot <= 1.0e300;
+                if (!sane || e_hit < 0 || !((e_base / q_tot) <= u - kMargin)) exact = true;     // same verdict in every CTA of every rank
+                if (dbg && t == dbg_step) dbg[2] = gtime_ns();
+                if (!exact) {
+                    const unsigned int ptag = A.tag_base | (++rnd_pick & 0xffffffu);
+                    const unsigned int pslot = rnd_pick & 1u;
+                    if (e_hit == A.rank * stride + grank) {       // the crossing is inside this CTA's rows
+                        int r_hit;
+                        double r_base, r_sum;
+                        block_locate(nrows, ct, cw, lane, u + kMargin, e_base, q_tot,
+                                     [&](int i) { return static_cast<double>(fmaxf(__ldcg(A.mind + seg.row_lo + i), 0.f)); },
+                                     ss.w, ss.hw, ss.bw, r_hit, r_base, r_sum);
+                        unsigned int word = 0xffffffffu;          // "not certain": everybody takes the exact path
+                        if (r_hit >= 0 && (r_base / q_tot) <= u - kMargin) word = static_cast<unsigned int>(seg.row_lo + r_hit);
+                        if (ct < A.world) ll_store(A.peer[ct] + G.pickw + pslot * 8, ptag, word);
+                        if (dbg && t == dbg_step && ct == 0) dbg[6] = gtime_ns();
+                    }
+                    if (ct == 0) ss.centre = static_cast<int>(ll_wait(win + G.pickw + pslot * 8, ptag, A));
+                    cons_bar();
+                    if (ss.centre == -1) exact = true;
+                    else centre = ss.centre;
+                    cons_bar();               // ss.centre is rewritten by the exact path
+                }
             }
-            if (prof) { const unsigned long long x1 = gtime_ns(); s_prof[3] += x1 - s_prof[7]; s_prof[7] = x1; }
-            if (dbg && t == dbg_step) dbg[2] = gtime_ns();
-            if (failed) {                                     // the same decision in every CTA of every rank
-                if (ct == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
-                centre = G.row_lo;
-            } else {
-                // ---- (3) fp64 mass of prob = clip(mind, 0) / S per leaf -> every rank ----
-                const unsigned int tag = A.tag_base | (++rnd_mass & 0xffffffu);
-                const unsigned int slot = rnd_mass & 1u;
-                if (my_leaf >= 0) {
-                    double m = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) m += prob64(v[j], total32);
-                    m += __shfl_down_sync(gmask, m, 1, 8);
-                    m += __shfl_down_sync(gmask, m, 2, 8);
-                    m += __shfl_down_sync(gmask, m, 4, 8);
-                    m = __shfl_sync(gmask, m, lane & ~7);
-                    if (g_lane < A.world) {
-                        char* dst = A.peer[g_lane] + G.massw + (static_cast<size_t>(slot) * K + my_leaf) * 16;
-                        ll_store(dst, tag, static_cast<unsigned int>(__double2hiint(m)));
-                        ll_store(dst + 8, tag, static_cast<unsigned int>(__double2loint(m)));
-                    }
-                }
-                if (dbg && t == dbg_step) dbg[3] = gtime_ns();
-                double* M = reinterpret_cast<double*>(val);   // K doubles == 2K floats
-                {
-                    unsigned int* M32 = reinterpret_cast<unsigned int*>(M);      // word 2i = hi, 2i + 1 = lo of leaf i
-                    ll_gather(win + G.massw + static_cast<size_t>(slot) * K * 16, 2 * K, 8, tag, 32, A, ct,
-                              [&](int i, unsigned long long w) { M32[i ^ 1] = static_cast<unsigned int>(w); });   // little endian: lo first
-                }
-                if (dbg && t == dbg_step) dbg[4] = gtime_ns();
-                if (ct == 0) { sh_hit = 0x7fffffff; sh_nz = -1; }
-                cons_bar();
-                // ---- np.random.choice == first k with cumsum64(p)[k] / total > u: locate the leaf.  One fixed
-                //      chain (thread chunks -> lanes -> warps), identical in every CTA of every rank. ----
-                const int per = (K + kConsThreads - 1) / kConsThreads;
-                const int l0 = min(K, ct * per), l1 = min(K, l0 + per);
-                double loc = 0.0;
-                for (int l = l0; l < l1; ++l) loc += M[l];
-                double inc = loc;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double w = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += w;
-                }
-                if (lane == 31) sh_w[cw] = inc;
-                const double prev = __shfl_up_sync(0xffffffffu, inc, 1);
-                cons_bar();
-                double woff = 0.0, total = 0.0;
-                for (int w = 0; w < kConsWarps; ++w) {
-                    if (w == cw) woff = total;
-                    total += sh_w[w];
-                }
-                double run = woff + (lane ? prev : 0.0);
-                int my_hit = 0x7fffffff, my_nz = -1;
-                double hit_base = 0.0, nz_base = 0.0;
-                for (int l = l0; l < l1; ++l) {
-                    const double before = run;
-                    run += M[l];
-                    if (M[l] > 0.0) { my_nz = l; nz_base = before; }
-                    if (my_hit == 0x7fffffff && (run / total) > u) { my_hit = l; hit_base = before; }
-                }
-                {
-                    const int wh = __reduce_min_sync(0xffffffffu, my_hit), wn = __reduce_max_sync(0xffffffffu, my_nz);
-                    if (lane == 0) {
-                        if (wh != 0x7fffffff) atomicMin(&sh_hit, wh);
-                        if (wn >= 0) atomicMax(&sh_nz, wn);
-                    }
-                }
-                cons_bar();
-                if (my_hit != 0x7fffffff && my_hit == sh_hit) sh_base = hit_base;
-                if (my_nz >= 0 && my_nz == sh_nz) sh_base_nz = nz_base;
-                cons_bar();
-                int leaf = sh_hit;
-                double base = sh_base;
-                if (leaf == 0x7fffffff) { leaf = sh_nz; base = sh_base_nz; }   // u beyond the last mass by an ulp
-                if (prof) { const unsigned long long x2 = gtime_ns(); s_prof[4] += x2 - s_prof[7]; s_prof[7] = x2; }
-                if (dbg && t == dbg_step) dbg[5] = gtime_ns();
-                // ---- (4) the group that owns the leaf searches inside it (values still in registers) ----
-                const unsigned int ptag = A.tag_base | (++rnd_pick & 0xffffffu);
-                const unsigned int pslot = rnd_pick & 1u;
-                if (leaf < 0 && grank == 0 && A.rank == 0 && cw == 0) {       // no mass at all: cannot happen with S > 0
-                    if (lane == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
-                    if (lane < A.world) ll_store(A.peer[lane] + G.pickw + pslot * 8, ptag, static_cast<unsigned int>(G.row_lo));
-                }
-                if (leaf >= 0 && leaf == my_leaf) {           // whole 8-lane group, uniformly
-                    // sequential order k = 8j + lane: scan 8 lanes per j, carry across j
-                    double carry = base;
-                    int hit = -1, nz = -1;
-                    const int g0 = lane & ~7;
-                    for (int j = 0; j < 16 && 8 * j < leaf_len; ++j) {
-                        double pj = 0.0;
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj)
-                            if (jj == j) pj = prob64(v[jj], total32);
-                        double sc = pj;
-#pragma unroll
-                        for (int o = 1; o < 8; o <<= 1) {
-                            const double w = __shfl_up_sync(gmask, sc, o, 8);
-                            if (g_lane >= o) sc += w;
-                        }
-                        const double rk = carry + sc;
-                        const bool cross = pj > 0.0 ? ((rk / total) > u) : false;
-                        // an element with zero mass can cross only if an earlier one did: ignore it
-                        const unsigned cb = (__ballot_sync(gmask, cross) >> g0) & 0xffu;
-                        const unsigned zb = (__ballot_sync(gmask, pj > 0.0) >> g0) & 0xffu;
-                        if (zb) nz = 8 * j + (31 - __clz(zb));
-                        if (cb) { hit = 8 * j + (__ffs(cb) - 1); break; }
-                        carry = __shfl_sync(gmask, rk, g0 + 7);
-                    }
-                    const int k = hit >= 0 ? hit : nz;        // no crossing: re-association moved it by an ulp
-                    int row = k >= 0 ? s_rows[grp * 128 + k] : -1;
-                    if (row < 0) {
-                        if (g_lane == 0) atomicCAS(A.status, 0, ALQ_ERR_NUMERIC);
-                        row = G.row_lo;
-                    }
-                    if (g_lane < A.world) ll_store(A.peer[g_lane] + G.pickw + pslot * 8, ptag, static_cast<unsigned int>(row));
-                    if (A.prof != nullptr && g_lane == 0 && t == dbg_step) A.prof[8 + 8 * blockIdx.x + 6] = gtime_ns();
-                }
-                if (ct == 0) sh_centre = static_cast<int>(ll_wait(win + G.pickw + pslot * 8, ptag, A));
-                cons_bar();
-                centre = sh_centre;
-                if (prof) { const unsigned long long x3 = gtime_ns(); s_prof[5] += x3 - s_prof[7]; }
+            if (exact) {
+                unsigned int rnd[3] = {rnd_leaf, rnd_mass, rnd_pick};
+                centre = exact_draw(A, A.groups + seg.part, &ss, val, s_sched, s_rows, grank, vtag, u, rnd, my_leaf, leaf_pos, leaf_len, cand_mask);
+                rnd_leaf = rnd[0]; rnd_mass = rnd[1]; rnd_pick = rnd[2];
             }
         }
         if (grank == 0 && ct == 0) A.picks[G.pick_off + t] = centre;
         if (dbg && t == dbg_step) dbg[7] = gtime_ns();
         if (prof) {
             const unsigned long long t_c = gtime_ns();
-            if (t > 0) { s_prof[0] += s_prof[8] - s_prof[6]; s_prof[1] += t_c - s_prof[8]; }
+            if (t > 0) { ss.prof[0] += ss.prof[8] - ss.prof[6]; ss.prof[1] += t_c - ss.prof[8]; }
+            else ss.prof[4] = t_c - ss.prof[6];      // the t = 0 selection (no streaming)
         }
     }
     if (prof) {
-        A.prof[0] = s_prof[0];
-        A.prof[1] = s_prof[1];
+        A.prof[0] = ss.prof[0];
+        A.prof[1] = ss.prof[1];
         A.prof[2] = static_cast<unsigned long long>(G.budget > 1 ? G.budget - 1 : 0);
-        for (int i = 0; i < 4; ++i) A.prof[3 + i] = s_prof[2 + i];
+        for (int i = 0; i < 3; ++i) A.prof[3 + i] = ss.prof[2 + i];
+        A.prof[6] = gtime_ns() - ss.prof[9];     // the whole kernel as CTA 0 saw it
     }
 }
 
@@ -709,11 +862,11 @@ struct PairTree {
 };
 
 template <bool FACTORED, bool SAMPLE>
-cudaError_t launch_persist(int grid, size_t smem, cudaStream_t st, PersistArgs& A, PipeCfg& cfg, int& k_max, int& lc_max) {
+cudaError_t launch_persist(int grid, size_t smem, cudaStream_t st, PersistArgs& A, PipeCfg& cfg, int& k_max, int& lc_max, int& ne_max) {
     auto* fn = greedy_persist_kernel<FACTORED, SAMPLE>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    void* args[] = {&A, &cfg, &k_max, &lc_max};
+    void* args[] = {&A, &cfg, &k_max, &lc_max, &ne_max};
     return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fn), dim3(grid), dim3(32 * (1 + kConsWarps)), args, smem, st);
 }
 
@@ -882,12 +1035,15 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         }
     }
 
+    k_max = (k_max + 1) & ~1;                 // keeps the doubles behind the tree schedule 8-byte aligned
     // ---- shared-memory plan: centre + ring + tree ---------------------------------------------------------
     PipeCfg cfg{};
     size_t smem = 0;
+    int ne_max = 1;
     {
         const size_t centre_bytes = static_cast<size_t>((d + c + 31) & ~31) * 4;
-        const size_t tree_bytes = sample ? static_cast<size_t>(k_max) * 12 + static_cast<size_t>(lc_max) * 512 + 64 : 64 + 12 + 512;
+        for (int p = 0; p < P; ++p) ne_max = std::max(ne_max, world * groups[p].seg_stride);
+        const size_t tree_bytes = (sample ? static_cast<size_t>(k_max) * 12 + static_cast<size_t>(lc_max) * 512 + 64 : 64 + 12 + 512) + static_cast<size_t>(ne_max) * 8;
         const size_t fixed = centre_bytes + tree_bytes + kConsWarps * 16 + 256;
         const size_t budget_bytes = ctx->smem_optin > 8192 ? ctx->smem_optin - 1536 : 0;
         size_t tile_target = 32 * 1024;
@@ -918,6 +1074,7 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         if (sample) {
             g.leafw = static_cast<unsigned int>(woff); woff = up(woff + static_cast<size_t>(2) * g.n_leaves * 8);
             g.massw = static_cast<unsigned int>(woff); woff = up(woff + static_cast<size_t>(2) * g.n_leaves * 16);
+            g.umw = static_cast<unsigned int>(woff);   woff = up(woff + static_cast<size_t>(2) * world * g.seg_stride * 16);
         }
     }
     const size_t win_bytes = woff;
@@ -995,14 +1152,16 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     int clock_khz = 1900000;
     cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, ctx->device);
     A.timeout_cycles = static_cast<long long>(ctx->spin_timeout_ms) * clock_khz;
+    A.fast_path = ctx->d2_fast_path;
+    if (const char* e = getenv("ALQ_D2_FAST_PATH")) A.fast_path = atoi(e) != 0;
 
     if (comm) {
         persist_ready_kernel<<<1, 32, 0, st>>>(A);       // after the clears above, in stream order
         ALQ_LAUNCH_CHECK(ctx);
     }
     cudaError_t le;
-    if (factored) le = sample ? launch_persist<true, true>(grid, smem, st, A, cfg, k_max, lc_max) : launch_persist<true, false>(grid, smem, st, A, cfg, k_max, lc_max);
-    else le = sample ? launch_persist<false, true>(grid, smem, st, A, cfg, k_max, lc_max) : launch_persist<false, false>(grid, smem, st, A, cfg, k_max, lc_max);
+    if (factored) le = sample ? launch_persist<true, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max) : launch_persist<true, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max);
+    else le = sample ? launch_persist<false, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max) : launch_persist<false, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max);
     if (le != cudaSuccess) {
         cudaGetLastError();
         ALQ_FAIL(ctx, ALQ_ERR_CUDA, "alq_greedy_select: cooperative launch failed: %s (grid %d, %zu B shared)", cudaGetErrorString(le), grid, smem);
@@ -1022,7 +1181,10 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         D->step_kernel_ms_host[1] = static_cast<float>(prof[1] * 1e-6 / steps);
         D->step_kernel_ms_host[2] = static_cast<float>(prof[2]);
         D->step_kernel_ms_host[3] = 3.0f;
-        for (int i = 0; i < 4; ++i) D->step_kernel_ms_host[4 + i] = static_cast<float>(prof[3 + i] * 1e-6 / steps);
+        D->step_kernel_ms_host[4] = static_cast<float>(prof[3] * 1e-6 / steps);
+        D->step_kernel_ms_host[5] = static_cast<float>(prof[4] * 1e-6 / steps);
+        D->step_kernel_ms_host[6] = static_cast<float>(prof[5] * 1e-6);      // t = 0 selection, ms
+        D->step_kernel_ms_host[7] = static_cast<float>(prof[6] * 1e-6);      // whole kernel, ms
     }
     if (D->step_kernel_ms_host && getenv("ALQ_PERSIST_DEBUG")) {      // per-CTA stamps of the middle step: where does the grid wait?
         std::vector<unsigned long long> h(8 * static_cast<size_t>(grid));

@@ -47,6 +47,8 @@ const char* alq_last_error(const alq_ctx* ctx);
 /* Implementation knobs (defaults pick the fastest valid kernel):
  *   "k3_impl"        0 auto | 1 exact-fp32 SIMT contraction | 2 tcgen05 3xTF32 contraction
  *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline | 3 persistent cooperative loop
+ *   "d2_fast_path"   1 (default): the persistent loop's D^2 draw first tries the certified path (one fp64 mass per CTA, the
+ *                    rounding of NumPy's float32 probabilities bounded by a margin); 0: always the exact NumPy-tree machinery
  *   "spin_timeout_ms" how long a kernel waits for a peer GPU's flag before giving up with ALQ_ERR_STATE (default 20000)
  *   "select_impl"    0 auto | 1 multi-kernel radix select   | 2 single cluster-resident launch
  *   "base_impl"      0 auto | 1 sequential class loop       | 2 per-class candidate lists + in-order resolve */
@@ -200,8 +202,8 @@ typedef struct alq_greedy_desc {
     /* optional timing out-parameter (forces a stream synchronisation at the end of the call), 8 floats in ms:
        [0] mean time of the streaming phase of a step (variants 1/2: CUDA events around the step kernel; variant 3:
        %globaltimer stamps taken by CTA 0), [1] mean time of the selection phase (barrier + exchange + draw) of a step
-       (variant 3 only), [2] steps measured, [3] the variant that ran, [4..7] variant 3, D^2 draw: mean time CTA 0 spends
-       waiting for its leaf's values / leaf sums + tree fold / leaf masses + scan / in-leaf search + pick. */
+       (variant 3 only), [2] steps measured, [3] the variant that ran, [4..7] variant 3 diagnostics: [4] [5] reserved, [6] the t = 0
+       selection in ms, [7] the whole kernel in ms as its CTA 0 saw it. */
     float* step_kernel_ms_host;
 } alq_greedy_desc;
 

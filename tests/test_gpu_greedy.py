@@ -20,7 +20,22 @@ def _split(feat, ind):
 
 
 def _run(eng, feat, ind, b, randomize=False, uniforms=None, variant=0, first=None, factors=None):
-    """Reference-shaped call: dense rows `feat`, boolean labeled indicator -> picks as rows of feat."""
+    """Reference-shaped call: dense rows `feat`, boolean labeled indicator -> picks as rows of feat.
+    The persistent loop's D^2 draw (variant 3) is run twice -- certified fast path first (default) and exact
+    NumPy-tree machinery only -- and both must give the same list."""
+    if randomize and variant == 3:
+        try:
+            eng.set_option("d2_fast_path", 0)
+            exact = _run_once(eng, feat, ind, b, randomize, uniforms, variant, first, factors)
+        finally:
+            eng.set_option("d2_fast_path", 1)
+        fast = _run_once(eng, feat, ind, b, randomize, uniforms, variant, first, factors)
+        assert fast == exact, "certified fast path and exact path disagree"
+        return fast
+    return _run_once(eng, feat, ind, b, randomize, uniforms, variant, first, factors)
+
+
+def _run_once(eng, feat, ind, b, randomize=False, uniforms=None, variant=0, first=None, factors=None):
     cand, lab, X, Y = _split(feat, ind)
     xn = eng.row_norm2(X)
     XA = YA = xan = yan = None

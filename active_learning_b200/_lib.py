@@ -64,6 +64,7 @@ SIGNATURES = {
     "alq_topb_pack": (C.c_int, [C.c_void_p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "alq_topb_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_i32p, C.c_void_p]),
     "alq_topb_exchange": (C.c_int, [C.c_void_p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.c_int64, c_i32p, C.c_void_p]),
+    "alq_comm_check": (C.c_int, [C.c_void_p]),
     "alq_uncertainty_query_host": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int32,
                                              C.c_int64, c_i32p]),
     "alq_badge_factors": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64, C.c_int32,

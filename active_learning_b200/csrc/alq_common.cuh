@@ -40,11 +40,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// bounded spin: a dead peer must not hang the GPU (sets a sticky status instead)
-__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want, int* status) {
+// bounded spin: a dead peer must not hang the GPU (sets a sticky status instead); callers must stop consuming
+// the window when it returns false.  timeout_cycles comes from the context option "spin_timeout_ms".
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want, int* status,
+                                          long long timeout_cycles) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) != want) {
-        if (clock64() - t0 > 8000000000LL) { if (status) atomicExch(status, ALQ_ERR_STATE); return false; }
+        if (clock64() - t0 > timeout_cycles) {
+            if (status) { *reinterpret_cast<volatile int*>(status) = ALQ_ERR_STATE; __threadfence_system(); }   // may be a mapped host word
+            return false;
+        }
         __nanosleep(64);
     }
     return true;
@@ -57,6 +62,8 @@ struct alq_ctx {
     cudaStream_t side_stream = nullptr;   // H2D pipelining for the *_host entry points
     cudaStream_t side_stream2 = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    int* xchg_status_host = nullptr;      // pinned + mapped: sticky status of the asynchronous peer-window exchanges
+    int* xchg_status_dev = nullptr;       // its device alias
     // grow-only scratch arenas (device) and pinned host staging
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

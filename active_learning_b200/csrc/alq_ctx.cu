@@ -32,6 +32,12 @@ extern "C" int alq_create(alq_ctx** out, int device) {
     cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking);
     cudaEventCreate(&ctx->ev_a);
     cudaEventCreate(&ctx->ev_b);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->xchg_status_host), sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+        *ctx->xchg_status_host = 0;
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->xchg_status_dev), ctx->xchg_status_host, 0);
+    } else {
+        cudaGetLastError();
+    }
     *out = ctx;
     return ALQ_OK;
 }
@@ -44,6 +50,7 @@ extern "C" void alq_destroy(alq_ctx* ctx) {
     if (ctx->arena2) cudaFree(ctx->arena2);
     if (ctx->tile_counters) cudaFree(ctx->tile_counters);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->xchg_status_host) cudaFreeHost(ctx->xchg_status_host);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->side_stream2) cudaStreamDestroy(ctx->side_stream2);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -89,6 +96,7 @@ int alq_scratch_reserve(alq_ctx* ctx, size_t bytes) {
 int alq_pinned_reserve(alq_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->pinned_bytes) return ALQ_OK;
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->xchg_status_host) cudaFreeHost(ctx->xchg_status_host);
     ctx->pinned = nullptr;
     ctx->pinned_bytes = 0;
     if (cudaMallocHost(&ctx->pinned, bytes) != cudaSuccess) {

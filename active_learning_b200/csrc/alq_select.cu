@@ -495,7 +495,8 @@ struct TopbXchg {
     size_t words_off, flags_off;      // this call's parity half of the reserved region
     unsigned long long tag;
     unsigned int* ticket;
-    int* status;
+    int* status;                      // mapped host word: sticky, read by the host at the next group call / alq_comm_check
+    long long timeout_cycles;
 };
 
 __global__ void __launch_bounds__(256)
@@ -522,13 +523,20 @@ topb_push_kernel(const float* __restrict__ scores, const int32_t* __restrict__ p
 
 __global__ void __launch_bounds__(256)
 topb_wait_merge_kernel(TopbXchg X, int64_t len, int32_t* __restrict__ out_pos, int64_t keep) {
-    if (threadIdx.x == 0)
-        for (int r = 0; r < X.world; ++r)
-            wait_flag(reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.flags_off) + r, X.tag, X.status);
+    __shared__ bool ok;
+    if (threadIdx.x == 0) {
+        ok = true;
+        for (int r = 0; r < X.world && ok; ++r)
+            ok = wait_flag(reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.flags_off) + r, X.tag, X.status, X.timeout_cycles);
+    }
     __syncthreads();
     const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(X.peer[X.rank] + X.words_off);
     const int lists = X.world;
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (!ok) {                        // a peer never showed up: nothing in the window may be trusted
+        if (i < keep) out_pos[i] = -1;
+        return;
+    }
     if (i >= lists * len) return;
     const unsigned long long key = __ldcg(keys + i);
     if (key == ~0ull) return;
@@ -566,14 +574,16 @@ extern "C" int alq_topb_exchange(alq_ctx* ctx, const float* scores, const int32_
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_topb_exchange: bad arguments (k=%lld b=%lld, b <= %zu)", (long long)k, (long long)b,
                  AlqComm::kTopbWords);
     if (G.bytes < 2 * G.topb_region_bytes()) ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_topb_exchange: peer window too small");
+    if (!ctx->xchg_status_dev) ALQ_FAIL(ctx, ALQ_ERR_STATE, "alq_topb_exchange: no mapped status word (cudaHostAlloc failed at alq_create)");
+    // a previous (asynchronous) exchange that timed out is reported here, before its garbage can be built upon
+    if (int rc0 = alq_comm_check(ctx)) return rc0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = alq_scratch_reserve(ctx, scratch_need({8, 8}));
+    int rc = alq_scratch_reserve(ctx, scratch_need({8}));
     if (rc) return rc;
     ScratchCursor cur(ctx->scratch);
     unsigned int* ticket = cur.take<unsigned int>(1);
-    int* status = cur.take<int>(1);
+    int* status = ctx->xchg_status_dev;
     ALQ_CUDA(ctx, cudaMemsetAsync(ticket, 0, 4, st));
-    ALQ_CUDA(ctx, cudaMemsetAsync(status, 0, 4, st));
     G.epoch += 1;
     TopbXchg X{};
     X.world = G.world; X.rank = G.rank;
@@ -584,12 +594,29 @@ extern "C" int alq_topb_exchange(alq_ctx* ctx, const float* scores, const int32_
     X.flags_off = base + static_cast<size_t>(G.world) * AlqComm::kTopbWords * 8;
     X.tag = G.epoch << 32;
     X.ticket = ticket; X.status = status;
+    int clock_khz = 1900000;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, ctx->device);
+    X.timeout_cycles = static_cast<long long>(ctx->spin_timeout_ms) * clock_khz;
     const int blocks = static_cast<int>((b + 255) / 256);
     topb_push_kernel<<<blocks, 256, 0, st>>>(scores, pos, k, row_lo, b, X);
     ALQ_LAUNCH_CHECK(ctx);
     topb_wait_merge_kernel<<<static_cast<int>((G.world * b + 255) / 256), 256, 0, st>>>(X, b, out_gpos, b);
     ALQ_LAUNCH_CHECK(ctx);
     return ALQ_OK;
+}
+
+// Sticky status of the asynchronous peer-window exchanges (alq_topb_exchange): the kernels write it straight into a
+// mapped host word, so reading it costs nothing -- but it is only final once the caller has synchronised the stream
+// the exchange ran on (e.g. after copying its result to the host).  Returns ALQ_OK, or ALQ_ERR_STATE (and clears it) if
+// a peer's flag never arrived within "spin_timeout_ms": the positions that exchange produced were all set to -1.
+extern "C" int alq_comm_check(alq_ctx* ctx) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (!ctx->xchg_status_host) return ALQ_OK;
+    const int s = *reinterpret_cast<volatile int*>(ctx->xchg_status_host);
+    if (s == 0) return ALQ_OK;
+    *reinterpret_cast<volatile int*>(ctx->xchg_status_host) = 0;
+    ALQ_FAIL(ctx, ALQ_ERR_STATE, "peer-window exchange timed out waiting for a peer GPU's flag (spin_timeout_ms = %d): its result is invalid",
+             ctx->spin_timeout_ms);
 }
 
 // Host-buffer entry point: H2D of the logits in row chunks on two side streams, K1 on each chunk

@@ -141,6 +141,11 @@ class Engine:
                                                _ptr(out), self._stream()), "alq_topb_exchange")
         return out
 
+    def comm_check(self):
+        """Raises AlqError if an asynchronous peer-window exchange (topb_exchange) timed out waiting for a peer.  Only
+        final after the stream the exchange ran on has been synchronised (e.g. by copying its result to the host)."""
+        self._check(self.lib.alq_comm_check(self._h), "alq_comm_check")
+
     def uncertainty_query_host(self, logits_host: torch.Tensor, mode: int, b: int) -> np.ndarray:
         """Host-buffer entry point (H2D + K1 + K1b + D2H inside the library)."""
         if logits_host.is_cuda or logits_host.dtype != torch.float32 or not logits_host.is_contiguous():

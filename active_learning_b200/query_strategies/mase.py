@@ -34,7 +34,7 @@ class MASEQuery(EngineMixin):
             lo, hi = group.row_range(len(idxs_for_query))
             min_margins, _, _ = self._margins_device(idxs_for_query[lo:hi], want_per_class=False)
             pos_loc = eng.select_smallest(min_margins, min(budget, hi - lo))
-            pos = group.merge_smallest(min_margins, pos_loc, lo, budget, eng)
+            pos = group.merge_smallest(min_margins, pos_loc, lo, budget, eng, rendezvous=True)
         else:
             min_margins, _, _ = self._margins_device(idxs_for_query, want_per_class=False)
             pos = eng.select_smallest(min_margins, budget).cpu().numpy()

@@ -165,9 +165,18 @@ class EngineMixin:
 
     @staticmethod
     def _encoder_fingerprint(net):
+        """Every parameter AND buffer of the encoder (BatchNorm running statistics included): a partially loaded
+        checkpoint, changed BN statistics or a fine-tuned last block must invalidate the cached embeddings.  Two
+        moments per tensor in fp64; runs once per query (a few ms for ResNet-50)."""
         with torch.no_grad():
-            ps = list(net.encoder.parameters())
-            return (len(ps), float(sum(p.double().sum() for p in ps[:4]))) if ps else (0, 0.0)
+            sd = net.encoder.state_dict()
+            if not sd:
+                return (0,)
+            fp = [len(sd)]
+            for name, t in sd.items():
+                t64 = t.detach().double().flatten()
+                fp.append((name, tuple(t.shape), float(t64.sum()), float((t64 * t64).sum())))
+            return tuple(fp)
 
     def _forward_pool_cached(self, idxs, net, want_features):
         """Same outputs as `_forward_pool`, but the encoder runs only for pool rows it has not seen: the

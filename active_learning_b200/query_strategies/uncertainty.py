@@ -52,7 +52,7 @@ class UncertaintyQuery(EngineMixin):
         scores = eng.score_softmax(logits, self.MODE)
         b_loc = min(budget, hi - lo)
         pos_loc = eng.select_smallest(scores, b_loc)
-        return group.merge_smallest(scores, pos_loc, lo, budget, eng)
+        return group.merge_smallest(scores, pos_loc, lo, budget, eng, rendezvous=True)
 
 
 class MarginQuery(UncertaintyQuery):

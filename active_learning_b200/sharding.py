@@ -76,19 +76,36 @@ class ShardGroup:
         lo = r * base + min(r, rem)
         return lo, lo + base + (1 if r < rem else 0)
 
-    def merge_smallest(self, scores_local, pos_local, row_lo, budget, engine, to_host=True):
+    def merge_smallest(self, scores_local, pos_local, row_lo, budget, engine, to_host=True, rendezvous=False):
         """Global `budget` smallest (score, global position) pairs from every rank's local winners.
 
         scores_local: this rank's score vector; pos_local: its local top-B positions (K1b output);
         row_lo: global position of local row 0.  Each rank packs its winners into 64-bit words
         (order-preserving score key << 32 | global position), ONE all-gather moves G*B words, and
         every rank runs the same device merge: ascending words == ascending (score, position), i.e.
-        exactly the single-GPU K1b order.  Only the B winning positions go to the host."""
+        exactly the single-GPU K1b order.  Only the B winning positions go to the host.
+
+        rendezvous: the peer-window exchange waits for every rank's flag with a bounded spin ("spin_timeout_ms");
+        after a phase in which ranks can drift apart by seconds (the per-shard forward pass of a sampler) pass True:
+        one barrier first, so that the spin only ever covers kernel-scale skew."""
         b = int(budget)
         if getattr(engine, "comm_ready", False) and b <= 16384:
             # peer-memory windows (Engine.comm_init): packed winners are stored straight into every rank's window
-            out = engine.topb_exchange(scores_local, pos_local, row_lo, b)
-            return out if not to_host else out.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            if rendezvous:
+                dist.barrier(group=self.pg)
+            try:
+                out = engine.topb_exchange(scores_local, pos_local, row_lo, b)
+                if not to_host:
+                    return out            # asynchronous: a timed-out exchange fills `out` with -1 and is reported by
+                                          # Engine.comm_check() / the next exchange
+                host = out.cpu().numpy()  # synchronises the stream: the status word is final now
+                engine.comm_check()
+                return host.astype(np.int64) & 0xFFFFFFFF
+            except Exception as exc:      # a peer never raised its flag: fall back to the collective path below
+                from ._lib import AlqError
+                if not isinstance(exc, AlqError):
+                    raise
+                self.exchange_failures = getattr(self, "exchange_failures", 0) + 1
         key = (b, scores_local.device)
         if self._buf.get("key") != key:
             self._buf = {"key": key,

@@ -96,6 +96,12 @@ int alq_topb_merge(alq_ctx* ctx, const uint64_t* keys, int64_t n, int64_t list_l
  * group must call it, in the same order relative to its other group calls.                      */
 int alq_topb_exchange(alq_ctx* ctx, const float* scores, const int32_t* pos, int64_t k, int64_t row_lo,
                       int64_t b, int32_t* out_gpos, void* stream);
+/* alq_topb_exchange is asynchronous, so a peer that never raises its flag (a dead or badly delayed rank; the bounded
+ * spin lasts "spin_timeout_ms") cannot be reported by its return value: the merge then writes -1 into every output
+ * position and records ALQ_ERR_STATE in a host-visible status word.  alq_comm_check returns (and clears) that status;
+ * call it once the stream has been synchronised (e.g. after the positions were copied to the host).  The next
+ * alq_topb_exchange on the context also reports it before doing anything.                         */
+int alq_comm_check(alq_ctx* ctx);
 
 /* Same tail for HOST buffers (what a CPU-tensor caller of MarginSampler.query has): pinned or
  * pageable host logits -> chunked H2D overlapped with K1 -> K1b -> positions back on the host.

@@ -1,19 +1,14 @@
 #!/bin/bash
-# the driver's scaling sequence on one 8-GPU box: N = 1, 2, 4, 8
+# bench.py under torchrun for N GPUs (gpurun --gpus N); prints the greedy workloads' summary
+N=${1:-2}
 mkdir -p gpurun_out
-timeout 600 python bench.py --gpus 1 --steps 50 --warmup 3 > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err; echo "N=1 exit=$?"
-for N in 2 4 8; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N \
-     bench.py --gpus $N --steps 50 --warmup 3 > gpurun_out/scale_n$N.json 2> gpurun_out/scale_n$N.err; echo "N=$N exit=$?"
-done
-python - <<'PY'
+if [ "$2" == "pytest" ]; then timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/r2_pytest_multi_n$N.txt; fi
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
+tail -3 gpurun_out/r2_bench_n$N.err
+python - <<PY
 import json
-for n in (1,2,4,8):
-    try:
-        d=json.load(open(f"gpurun_out/scale_n{n}.json"))
-        w=d.get("workloads",{})
-        print(n, round(d["value"]/1e6,1),"M/s", round(d["ms_per_step"]*1e3,1),"us", "k1",round(d["roofline"]["frac"],3),
-              {k:(round(v.get("ms_per_step",0),1), round(v.get("breakdown_ms",{}).get("loop_ms",0)/10,1)) for k,v in w.items()})
-    except Exception as e:
-        print(n,"ERR",e)
+d=json.load(open('gpurun_out/r2_bench_n$N.json'))
+print({k:d[k] for k in ('n_gpus','value','ms_per_step','host_enqueue_ms_per_step')}, d['roofline']['frac'])
+for k,v in d.get('workloads',{}).items():
+    if isinstance(v,dict): print(k, {a:v.get(a) for a in ('error','value','ms_per_step','us_per_selection_step','picks_match_single_gpu','breakdown_ms')}, (v.get('roofline') or {}).get('frac'), (v.get('roofline') or {}).get('streaming_phase'))
 PY

@@ -74,6 +74,8 @@ struct alq_ctx {
     int64_t launches = 0;
     unsigned int* tile_counters = nullptr;   // ring of per-launch tile counters (dynamic scheduling of K1/K2)
     int tile_counter_next = 0;
+    unsigned int* sel_ring = nullptr;        // ring of zeroed per-launch scratch of the fused score+select kernel
+    int sel_ring_next = 0;
     AlqComm comm;
     int k3_impl = 0;          // 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32
     int select_impl = 0;      // 0 auto, 1 multi-kernel radix select, 2 cluster-resident single launch

@@ -49,6 +49,7 @@ extern "C" void alq_destroy(alq_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->arena2) cudaFree(ctx->arena2);
     if (ctx->tile_counters) cudaFree(ctx->tile_counters);
+    if (ctx->sel_ring) cudaFree(ctx->sel_ring);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->xchg_status_host) cudaFreeHost(ctx->xchg_status_host);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);

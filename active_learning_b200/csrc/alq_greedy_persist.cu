@@ -213,10 +213,14 @@ __device__ __forceinline__ void block_locate(int n, int ct, int cw, int lane, do
     double run = base0 + woff + (lane ? prev : 0.0);
     int hit = -1;
     double hb = 0.0;
+    // (run / total) > u_hi decided without the fp64 division wherever that is safe: the product u_hi * total is within
+    // one ulp of the real threshold and the quotient is correctly rounded, so outside a band of a few ulps around it the
+    // comparison of `run` with the product gives the division's answer; inside the band the division itself is done
+    const double thr = u_hi * total, thr_lo = thr * (1.0 - 8e-16), thr_hi = thr * (1.0 + 8e-16);
     for (int i = i0; i < i1; ++i) {
         const double before = run, m = mass(i);
         run += m;
-        if (hit < 0 && m > 0.0 && (run / total) > u_hi) { hit = i; hb = before; }
+        if (hit < 0 && m > 0.0 && run > thr_lo && (run > thr_hi || (run / total) > u_hi)) { hit = i; hb = before; }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, hit >= 0);
     const int src = bal ? __ffs(bal) - 1 : 0;

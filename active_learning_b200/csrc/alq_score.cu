@@ -146,6 +146,112 @@ __device__ __forceinline__ void load_row_smem(const float4* p, int lane, int nve
     }
 }
 
+// ---- fused stable top-B (K1 + K1b in ONE cooperative launch) ---------------------------------------------------
+// The scoring kernel already runs one CTA per SM; with the selection as a separate launch the step paid a 43 us
+// 8-SM cluster kernel plus launch gaps behind a 56 us stream.  Fused: every CTA keeps the (key, row) words of the rows
+// it scored in shared memory and counts their 11 top key bits on the way; after the stream
+//   E1 the per-CTA histograms are added into a global one (red.add), grid barrier;
+//   E2 every CTA finds the bin T that holds the b-th smallest key;
+//   E3 keeps its words with bin <= T (all of the winners plus the few other keys of bin T) and appends them to a
+//      global candidate list (one atomicAdd per CTA reserves the slots), grid barrier;
+//   E4 pulls the whole candidate list (b + a few words) into the shared memory the tile ring no longer needs and ranks
+//      its OWN candidates against it by counting (warp per candidate): rank < b  ->  out_pos[rank] = row.
+// Words are key << 32 | row, so the order is (score, position): exactly K1b's stable order
+// (`torch.sort(scores).indices[:B]`, margin_sampler.py:42), whatever the order the candidates were appended in.
+struct SelArgs {
+    int b;                          // 0: plain scoring kernel
+    int list_cap;                   // (key, row) words a CTA can hold
+    unsigned int* g_hist;           // [2048] zeroed
+    unsigned int* g_ctr;            // [4] zeroed: [0] grid-barrier arrivals, [1] candidates appended
+    unsigned long long* g_cand;     // [n]
+    int32_t* out_pos;               // [b]
+};
+
+__device__ __forceinline__ void sel_grid_barrier(unsigned int* ctr, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (static_cast<int>(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+// s_misc: [0] words in s_list, [1] threshold bin, [2] -, [3] offset in g_cand, [4] own candidates
+__device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist, unsigned long long* s_list, int* s_misc,
+                                             unsigned long long* buf, int buf_cap) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    __syncthreads();                                        // every consumer warp has appended its rows
+    for (int i = tid; i < 2048; i += nthr) {
+        const uint32_t h = s_hist[i];
+        if (h) atomicAdd(S.g_hist + i, h);
+    }
+    sel_grid_barrier(S.g_ctr, gridDim.x);
+    for (int i = tid; i < 2048; i += nthr) s_hist[i] = __ldcg(S.g_hist + i);
+    __syncthreads();
+    if (warp == 0) {                                        // bin of the b-th smallest key: 64 bins per lane
+        uint32_t loc = 0;
+        for (int k = 0; k < 64; ++k) loc += s_hist[lane * 64 + k];
+        uint32_t inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const uint32_t excl = inc - loc, b = static_cast<uint32_t>(S.b);
+        if (excl < b && b <= inc) {
+            uint32_t run = excl;
+            int T = lane * 64 + 63;
+            for (int k = 0; k < 64; ++k) {
+                run += s_hist[lane * 64 + k];
+                if (run >= b) { T = lane * 64 + k; break; }
+            }
+            s_misc[1] = T;
+        }
+    }
+    if (tid == 0) s_misc[4] = 0;
+    __syncthreads();
+    const uint32_t T = static_cast<uint32_t>(s_misc[1]);
+    const int cnt = s_misc[0];
+    for (int i = tid; i < cnt; i += nthr) {
+        const unsigned long long w = s_list[i];
+        if (static_cast<uint32_t>(w >> 53) <= T) buf[atomicAdd(&s_misc[4], 1)] = w;
+    }
+    __syncthreads();
+    const int nc = s_misc[4];
+    if (tid == 0) s_misc[3] = static_cast<int>(atomicAdd(S.g_ctr + 1, static_cast<unsigned int>(nc)));
+    __syncthreads();
+    const int off = s_misc[3];
+    for (int i = tid; i < nc; i += nthr) {
+        const unsigned long long w = buf[i];
+        s_list[i] = w;
+        S.g_cand[off + i] = w;
+    }
+    sel_grid_barrier(S.g_ctr, 2u * gridDim.x);
+    const int total = static_cast<int>(__ldcg(S.g_ctr + 1));
+    for (int i = tid; i < nc; i += nthr) s_hist[i] = 0;     // ranks of this CTA's candidates (nc <= list_cap <= 2048)
+    for (int base = 0; base < total; base += buf_cap) {
+        const int m = min(buf_cap, total - base);
+        __syncthreads();
+        for (int j = tid; j < m; j += nthr) buf[j] = __ldcg(S.g_cand + base + j);
+        __syncthreads();
+        for (int i = warp; i < nc; i += nwarp) {
+            const unsigned long long w = s_list[i];
+            int c = 0;
+            for (int j = lane; j < m; j += 32) c += buf[j] < w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) s_hist[i] += static_cast<uint32_t>(c);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nc; i += nthr) {
+        const uint32_t r = s_hist[i];
+        if (r < static_cast<uint32_t>(S.b)) S.out_pos[r] = static_cast<int32_t>(s_list[i] & 0xffffffffu);
+    }
+}
+
 // MODE 0..2: scores; MODE 3: BADGE factors (writes a[row, :] and a_norm2[row]);
 // MODE 4: MASE minimum margin + predicted class (K6, table reads pruned); MODE 5: MASE with the per-class radii written
 constexpr int MODE_MASE_MIN = 4, MODE_MASE_FULL = 5;
@@ -153,12 +259,20 @@ template <int NV, int MODE>
 __global__ void __launch_bounds__(1024, 1)
 rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg cfg, float* __restrict__ scores,
                  int bs, int64_t grow0, int64_t n_total, float* __restrict__ a, int64_t lda,
-                 unsigned int* __restrict__ tile_counter, MaseArgs mase) {
+                 unsigned int* __restrict__ tile_counter, MaseArgs mase, const __grid_constant__ SelArgs sel) {
     extern __shared__ __align__(128) unsigned char smem_rows[];
     float* tiles = reinterpret_cast<float*>(smem_rows);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(cfg.stages) * cfg.tile_floats);
     uint64_t* empty = full + cfg.stages;
     int* s_tile = reinterpret_cast<int*>(empty + cfg.stages);          // tile index carried by each stage (-1: done)
+    // fused selection (sel.b > 0): level-0 histogram, this CTA's (key, row) words, a few counters
+    unsigned long long* s_list = reinterpret_cast<unsigned long long*>(s_tile + ((cfg.stages + 1) & ~1));
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_list + sel.list_cap);
+    int* s_misc = reinterpret_cast<int*>(s_hist + 2048);
+    if (sel.b > 0) {
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
+        if (threadIdx.x < 8) s_misc[threadIdx.x] = 0;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = cfg.rows_per_tile;
     // Tiles are claimed dynamically (runs of kClaim consecutive tiles per atomicAdd): a CTA that starts late --
@@ -175,13 +289,15 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
     const int nvec = c >> 2;
     if (warp == 0) {
         if (lane == 0) {
-            int claim_lo = 0, claim_hi = 0, sentinels = 0;
+            int claim_lo = 0, claim_hi = 0, sentinels = 0, claimed = 0;
             bool exhausted = false;
             for (int i = 0;; ++i) {
                 const int s = i % cfg.stages;
                 const uint32_t round = static_cast<uint32_t>(i / cfg.stages);
                 if (round > 0) mbar_wait(&empty[s], (round - 1) & 1u);
+                if (claim_lo == claim_hi && !exhausted && sel.b > 0 && (claimed + kClaim) * R > sel.list_cap) exhausted = true;
                 if (claim_lo == claim_hi && !exhausted) {
+                    claimed += kClaim;
                     const unsigned int got = atomicAdd(tile_counter, static_cast<unsigned int>(kClaim));
                     if (got >= static_cast<unsigned int>(tiles_total)) exhausted = true;
                     else { claim_lo = static_cast<int>(got); claim_hi = min(tiles_total, claim_lo + kClaim); }
@@ -262,9 +378,17 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
             if (lane < rr && (lane % cfg.split) == sub) {
                 scores[row0 + lane] = my_score;
                 if (MODE >= MODE_MASE_MIN) mase.pred[row0 + lane] = my_pred;
+                if (sel.b > 0) {
+                    const uint32_t key = alq_ord(my_score + 0.0f);
+                    s_list[atomicAdd(&s_misc[0], 1)] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(row0 + lane);
+                    atomicAdd(&s_hist[key >> 21], 1u);
+                }
             }
         }
     }
+    if (sel.b > 0)       // every thread of the CTA (the tile ring is free now: it becomes the candidate buffer)
+        select_epilogue(sel, s_hist, s_list, s_misc, reinterpret_cast<unsigned long long*>(tiles),
+                        static_cast<int>(static_cast<size_t>(cfg.stages) * cfg.tile_floats / 2));
 }
 
 // Any c / alignment: two passes over the row, the second one hits L1/L2.
@@ -474,7 +598,7 @@ int rows_grid(const alq_ctx* ctx, int64_t n, int warps_per_block) {
 }
 
 // shared-memory plan of the pipelined kernels; false if the row does not fit
-bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem) {
+bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem, size_t reserve = 0) {
     const size_t row_bytes = static_cast<size_t>(c) * 4;
     if (row_bytes % 16 || row_bytes > 16384 || ctx->smem_optin < 64 * 1024) return false;
     size_t tile_target = 16384;
@@ -482,7 +606,7 @@ bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem) {
     int R = static_cast<int>(std::max<size_t>(1, tile_target / row_bytes));
     R = std::min(R, 32);
     const size_t tile = R * row_bytes;
-    int stages = static_cast<int>((ctx->smem_optin - 4096) / tile);
+    int stages = static_cast<int>((ctx->smem_optin - 4096 - reserve) / tile);
     stages = std::min(stages, 16);
     if (stages < 3) return false;
     int split = 2;
@@ -490,7 +614,7 @@ bool plan_row_pipe(const alq_ctx* ctx, int c, RowPipeCfg& cfg, size_t& smem) {
     while (split > 1 && (stages * split > 31 || split > R)) --split;
     cfg.rows_per_tile = R; cfg.stages = stages; cfg.consumers = stages * split; cfg.split = split;
     cfg.tile_floats = static_cast<int>(tile / 4);
-    smem = stages * tile + 2 * stages * sizeof(uint64_t) + stages * sizeof(int) + 128;
+    smem = stages * tile + 2 * stages * sizeof(uint64_t) + (stages + 1) * sizeof(int) + 128 + reserve;
     return true;
 }
 
@@ -512,7 +636,7 @@ unsigned int* next_tile_counter(alq_ctx* ctx, cudaStream_t st) {
 template <int NV, int MODE>
 cudaError_t launch_rows_pipe(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
                              int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda,
-                             const MaseArgs& mase = MaseArgs{}) {
+                             const MaseArgs& mase = MaseArgs{}, const SelArgs& sel = SelArgs{}) {
     cudaError_t e = cudaFuncSetAttribute(rows_pipe_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -520,21 +644,29 @@ cudaError_t launch_rows_pipe(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cf
     const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles_total));
     unsigned int* counter = next_tile_counter(ctx, st);
     if (!counter) return cudaErrorMemoryAllocation;
+    if (sel.b > 0) {     // the fused selection synchronises the grid: co-residency must be guaranteed
+        RowPipeCfg cfg_v = cfg;
+        MaseArgs mase_v = mase;
+        SelArgs sel_v = sel;
+        void* args[] = {&logits, &n, &c, &cfg_v, &scores, &bs, &row0, &n_total, &a, &lda, &counter, &mase_v, &sel_v};
+        return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rows_pipe_kernel<NV, MODE>), dim3(grid), dim3(32 * (1 + cfg.consumers)),
+                                           args, smem, st);
+    }
     rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, row0, n_total, a, lda,
-                                                                          counter, mase);
+                                                                          counter, mase, sel);
     return cudaGetLastError();
 }
 
 template <int MODE>
 cudaError_t launch_rows_pipe_nv(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cfg, size_t smem, const float* logits,
                                 int64_t n, int c, float* scores, int bs, int64_t row0, int64_t n_total, float* a, int64_t lda,
-                                const MaseArgs& mase = MaseArgs{}) {
+                                const MaseArgs& mase = MaseArgs{}, const SelArgs& sel = SelArgs{}) {
     const int nv = (c / 4 + 31) / 32;
-    if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
-    if (nv <= 2) return launch_rows_pipe<2, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
-    if (nv <= 4) return launch_rows_pipe<4, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
-    if (nv <= 8) return launch_rows_pipe<8, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
-    return launch_rows_pipe<16, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase);
+    if (nv <= 1) return launch_rows_pipe<1, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase, sel);
+    if (nv <= 2) return launch_rows_pipe<2, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase, sel);
+    if (nv <= 4) return launch_rows_pipe<4, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase, sel);
+    if (nv <= 8) return launch_rows_pipe<8, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase, sel);
+    return launch_rows_pipe<16, MODE>(ctx, st, cfg, smem, logits, n, c, scores, bs, row0, n_total, a, lda, mase, sel);
 }
 
 template <int NV>
@@ -595,6 +727,66 @@ extern "C" int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, i
         score_rows_generic_kernel<<<grid, kScoreThreads, 0, st>>>(logits, n, c, ld, mode, scores);
     }
     ALQ_LAUNCH_CHECK(ctx);
+    return ALQ_OK;
+}
+
+// zeroed scratch of one fused launch (2048-bin histogram + counters): slots of a ring cleared in bulk
+static unsigned int* next_sel_slot(alq_ctx* ctx, cudaStream_t st) {
+    constexpr int kSlots = 64, kWords = 2048 + 16;
+    if (!ctx->sel_ring) {
+        if (cudaMalloc(&ctx->sel_ring, static_cast<size_t>(kSlots) * kWords * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaMemset(ctx->sel_ring, 0, static_cast<size_t>(kSlots) * kWords * 4);
+        ctx->sel_ring_next = 0;
+    }
+    if (ctx->sel_ring_next == kSlots) {
+        cudaMemsetAsync(ctx->sel_ring, 0, static_cast<size_t>(kSlots) * kWords * 4, st);   // stream-ordered after its last users
+        ctx->sel_ring_next = 0;
+    }
+    return ctx->sel_ring + static_cast<size_t>(ctx->sel_ring_next++) * kWords;
+}
+
+extern "C" int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
+                                    int64_t b, float* scores, int32_t* out_pos, void* stream) {
+    if (!ctx) return ALQ_ERR_INVALID;
+    if (n < 0 || c <= 0 || ld < c || mode < 0 || mode > 2 || b < 0 || b > n)
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_tail: bad shape n=%lld c=%d ld=%lld mode=%d b=%lld", (long long)n, c,
+                 (long long)ld, mode, (long long)b);
+    if (n == 0 || b == 0) return ALQ_OK;
+    if (!logits || !scores || !out_pos) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_tail: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    constexpr int kListCap = 2048;
+    const size_t reserve = static_cast<size_t>(kListCap) * 8 + 2048 * 4 + 64;
+    RowPipeCfg cfg{};
+    size_t smem = 0;
+    const bool vec = (c % 4 == 0) && (ld == c) && aligned16(logits) && c <= 2048;
+    const bool fused = vec && n >= 4096 && n < (1LL << 31) && ctx->select_impl != 1 && ctx->greedy_variant != 1 &&
+                       n * 5 <= static_cast<int64_t>(ctx->sm_count) * kListCap * 4 &&       // the per-CTA lists absorb any imbalance
+                       plan_row_pipe(ctx, c, cfg, smem, reserve);
+    if (!fused) {                                   // two launches: K1 then K1b
+        int rc = alq_score_softmax(ctx, logits, n, c, ld, mode, scores, stream);
+        if (rc) return rc;
+        return alq_select_smallest(ctx, scores, n, b, out_pos, stream);
+    }
+    int rc = alq_scratch_reserve(ctx, scratch_need({static_cast<size_t>(n) * 8}));
+    if (rc) return rc;
+    SelArgs sel{};
+    sel.b = static_cast<int>(b);
+    sel.list_cap = kListCap;
+    unsigned int* slot = next_sel_slot(ctx, st);
+    if (!slot) ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_uncertainty_tail: scratch allocation failed");
+    sel.g_hist = slot;
+    sel.g_ctr = slot + 2048;
+    sel.g_cand = ScratchCursor(ctx->scratch).take<unsigned long long>(n);
+    sel.out_pos = out_pos;
+    cudaError_t e;
+    if (mode == ALQ_MODE_MARGIN) e = launch_rows_pipe_nv<ALQ_MODE_MARGIN>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0, MaseArgs{}, sel);
+    else if (mode == ALQ_MODE_LEAST_CONFIDENCE) e = launch_rows_pipe_nv<ALQ_MODE_LEAST_CONFIDENCE>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0, MaseArgs{}, sel);
+    else e = launch_rows_pipe_nv<ALQ_MODE_ENTROPY>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0, MaseArgs{}, sel);
+    ctx->launches++;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ALQ_FAIL(ctx, ALQ_ERR_CUDA, "alq_uncertainty_tail: cooperative launch failed: %s", cudaGetErrorString(e));
+    }
     return ALQ_OK;
 }
 

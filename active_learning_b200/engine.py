@@ -116,6 +116,17 @@ class Engine:
                                                  self._stream()), "alq_select_smallest")
         return out
 
+    def uncertainty_tail(self, logits: torch.Tensor, mode: int, b: int, scores_out: Optional[torch.Tensor] = None):
+        """K1 + K1b in one call (one cooperative launch when the fused path applies): (scores [n], positions [b] int32,
+        ascending (score, position))."""
+        logits = _f32c(logits, "logits")
+        n, c = logits.shape
+        scores = scores_out if scores_out is not None else torch.empty(n, dtype=torch.float32, device=logits.device)
+        out = torch.empty(int(b), dtype=torch.int32, device=logits.device)
+        self._check(self.lib.alq_uncertainty_tail(self._h, _ptr(logits), n, c, _ld(logits), mode, int(b), _ptr(scores), _ptr(out),
+                                                  self._stream()), "alq_uncertainty_tail")
+        return scores, out
+
     def topb_pack(self, scores: torch.Tensor, pos: torch.Tensor, row_lo: int, b_pad: int,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Local winners as packed (score key << 32 | global position) int64 words, ~0-padded to b_pad."""

@@ -36,10 +36,16 @@ class UncertaintyQuery(EngineMixin):
             logits, _ = self._forward_pool(idxs_for_query, self.net, want_features=False)
             self.net.train()                               # margin_sampler.py:38
             eng = self.get_engine()
-            scores = eng.score_softmax(logits, self.MODE)
-            pos = eng.select_smallest(scores, budget).cpu().numpy()
+            pos = self._tail(eng, logits, budget)[1].cpu().numpy()
         labeled_idxs = np.asarray(idxs_for_query)[pos].tolist()
         return labeled_idxs, budget
+
+    def _tail(self, eng, logits, b):
+        """(scores, positions of the b smallest in stable order): K1 + K1b, one fused launch where the engine has it."""
+        if hasattr(eng, "uncertainty_tail"):
+            return eng.uncertainty_tail(logits, self.MODE, b)
+        scores = eng.score_softmax(logits, self.MODE)
+        return scores, eng.select_smallest(scores, b)
 
     # -- row-sharded variant: every rank scores N/G rows, one exchange for the global top-B ------
     def _query_sharded(self, idxs_for_query, budget, group):
@@ -49,9 +55,8 @@ class UncertaintyQuery(EngineMixin):
         logits, _ = self._forward_pool(idxs_for_query[lo:hi], self.net, want_features=False)
         self.net.train()
         eng = self.get_engine()
-        scores = eng.score_softmax(logits, self.MODE)
         b_loc = min(budget, hi - lo)
-        pos_loc = eng.select_smallest(scores, b_loc)
+        scores, pos_loc = self._tail(eng, logits, b_loc)
         return group.merge_smallest(scores, pos_loc, lo, budget, eng, rendezvous=True)
 
 

@@ -49,12 +49,46 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_TF32 = {}
+
+
 def tf32_peak():
+    """Dense TF32 tensor peak, MEASURED here (it is not in MEASURED_PEAKS.json): cuBLAS TF32 GEMM
+    8192^3 through torch.matmul with allow_tf32, best of 10, CUDA events -- the same recipe as the driver's bf16 figure.
+    Only a denominator: nothing on the product path calls it.  Falls back to bf16 / 2 without a GPU."""
+    if "v" in _TF32:
+        return _TF32["v"]
+    val, src = None, None
     try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            return float(json.load(fh)["bf16_tflops"]) / 2.0
+        if torch.cuda.is_available():
+            old = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            n = 8192
+            a = torch.randn(n, n, device="cuda")
+            b = torch.randn(n, n, device="cuda")
+            best = float("inf")
+            for i in range(13):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                c = a @ b
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    best = min(best, e0.elapsed_time(e1))
+            del a, b, c
+            torch.backends.cuda.matmul.allow_tf32 = old
+            val, src = 2.0 * n ** 3 / (best * 1e-3) / 1e12, "measured in this run: cuBLAS TF32 GEMM 8192^3 (torch.matmul, allow_tf32), best of 10"
     except Exception:
-        return 1590.0 / 2.0
+        val = None
+    if val is None:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                val = float(json.load(fh)["bf16_tflops"]) / 2.0
+        except Exception:
+            val = 1590.0 / 2.0
+        src = "MEASURED_PEAKS.json bf16_tflops / 2 (no live TF32 measurement possible)"
+    _TF32["v"], _TF32["src"] = val, src
+    return val
 
 
 def ncu_traffic(kernel):
@@ -405,7 +439,121 @@ def run_greedy_workload(eng, kind, peak, steps, warmup, world=1, rank=0, check_p
                "bound": "tensor", "effective_fp32_tflops": flops / (acc["k3_ms"] * 1e-3) / 1e12,
                "achieved": 3 * flops / (acc["k3_ms"] * 1e-3) / 1e12, "unit": "TFLOP/s",
                "peak": tf32_peak(), "frac": 3 * flops / (acc["k3_ms"] * 1e-3) / 1e12 / tf32_peak(),
-               "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 issues at half the bf16 rate); 3 tf32 MMAs per fp32 product"},
+               "peak_source": _TF32.get("src"), "note": "3 tf32 MMAs per fp32 product; ncu sm__pipe_tensor_cycles_active of the same "
+                                                         "kernel is in profiles/README.md"},
+    }
+
+
+PART_P, PART_LAB, PART_UNL, PART_BUDGET = 10, 5000, 8000, 1000     # gen_jobs.py:11-13,19: --partitions 10, 50k + 80k rows
+
+
+def run_partitioned_workload(eng, kind, peak, steps, warmup, world=1, rank=0):
+    """The reference's own ImageNet configuration (gen_jobs.py:11-19, partitioned_coreset_sampler.py:52-84): 130 000
+    rows = 50 000 labeled + 80 000 unlabeled dealt into P = 10 partitions of 13 000 rows, 1 000 picks per partition.
+    PartitionedCoreset: 2048-d embeddings, arg-max.  PartitionedBADGE: pooled 512-d gradient embeddings (K2p), D^2 draw.
+    Partitions are independent: partition i runs on rank i % G (no collective inside the loop; the picks are gathered
+    once), each rank runs its partitions as ONE batched persistent launch.  Like-for-like with `cpu_baseline`."""
+    import torch.distributed as dist
+    dev = eng.device
+    badge = kind == "partitioned_badge"
+    dim = 512 if badge else EMB_DIM
+    mine = [i for i in range(PART_P) if i % world == rank]
+    rows = PART_LAB + PART_UNL
+
+    def data_for(i):
+        g = torch.Generator(device=dev).manual_seed(7000 + i)
+        f = torch.relu(torch.randn(rows, EMB_DIM, device=dev, generator=g))
+        return (f, torch.randn(rows, N_CLASSES, device=dev, generator=g) * 3 if badge else None, i)
+
+    local = [data_for(i) for i in mine]
+    rng = np.random.default_rng(11)
+    us_all = [rng.random(PART_BUDGET) for _ in range(PART_P)]
+    nloc = len(mine)
+    part_off = np.arange(nloc + 1, dtype=np.int32) * PART_UNL
+    vpos = torch.as_tensor(np.tile(np.arange(PART_LAB, rows, dtype=np.int32), max(nloc, 1)), device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    out = {}
+
+    def one(timed, budget=PART_BUDGET, which=None):
+        sel = local if which is None else which
+        if world > 1 and which is None:
+            dist.barrier()
+        if timed:
+            ev[0].record()
+        F = [eng.badge_pooled_embedding(lg, f, 128) for f, lg, _ in sel] if badge else [f for f, _, _ in sel]   # K2p
+        if timed:
+            ev[1].record()
+        picks = np.zeros(0, dtype=np.int32)
+        stream_ms = 0.0
+        if sel:
+            X = torch.cat([f[PART_LAB:] for f in F], dim=0)
+            xn = eng.row_norm2(X)
+            mind = torch.empty(X.shape[0], device=dev)
+            for j, f in enumerate(F):                            # K3 per partition
+                Y = f[:PART_LAB]
+                eng.min_dist(X[j * PART_UNL:(j + 1) * PART_UNL], xn[j * PART_UNL:(j + 1) * PART_UNL], Y, eng.row_norm2(Y),
+                             out=mind[j * PART_UNL:(j + 1) * PART_UNL])
+            if timed:
+                ev[2].record()
+            po = np.arange(len(sel) + 1, dtype=np.int32) * PART_UNL
+            picks, stream_ms = eng.greedy_select(
+                X, xn, mind, po, [budget] * len(sel),
+                uniforms=np.concatenate([us_all[pid][:budget] for _, _, pid in sel]) if badge else None,
+                vpos=vpos[:len(sel) * PART_UNL] if badge else None, full_n=[rows] * len(sel) if badge else None, time_steps=True)
+        elif timed:
+            ev[2].record()
+        if timed:
+            ev[3].record()
+            torch.cuda.synchronize()
+            out["prep_ms"], out["k3_ms"], out["loop_ms"] = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+            out["variant"] = eng.last_greedy_timing["variant"] if sel else None
+        return picks
+
+    picks = None
+    for _ in range(warmup):
+        picks = one(False)
+    acc = {}
+    for _ in range(steps):
+        picks = one(True)
+        for k in ("prep_ms", "k3_ms", "loop_ms"):
+            acc[k] = acc.get(k, 0.0) + out[k] / steps
+    ms = acc["prep_ms"] + acc["k3_ms"] + acc["loop_ms"]
+    per_part = [picks[j * PART_BUDGET:(j + 1) * PART_BUDGET] - j * PART_UNL for j in range(nloc)]
+    unique = all(len(set(p.tolist())) == PART_BUDGET for p in per_part)
+    match = None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {mine[j]: per_part[j].tolist() for j in range(nloc)})
+        allp = {k: v for d in gathered for k, v in d.items()}
+        # a partition's picks do not depend on the rank that runs it: every rank recomputes the first 150 picks of a
+        # partition that ANOTHER rank ran and compares
+        other = [i for i in range(PART_P) if i % world == (rank + 1) % world]
+        ok = 1
+        if other:
+            chk = one(False, budget=150, which=[data_for(other[0])])
+            ok = int(np.array_equal(chk, np.asarray(allp[other[0]][:150])))
+        same = torch.tensor([ok * int(len(allp) == PART_P)], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        match = bool(same.item())
+        t = torch.tensor([ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"]], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, acc["prep_ms"], acc["k3_ms"], acc["loop_ms"] = [float(v) for v in t]
+    nmax = max(len([i for i in range(PART_P) if i % world == r]) for r in range(world))
+    row_bytes = 4 * dim + 12
+    step_ms = acc["loop_ms"] / max(PART_BUDGET - 1, 1)
+    achieved = nmax * PART_UNL * row_bytes / (step_ms * 1e-3) / 1e9
+    return {
+        "workload": (f"{'PartitionedBADGESampler' if badge else 'PartitionedCoresetSampler'} tail, the reference's ImageNet job "
+                     f"(gen_jobs.py: {PART_P} partitions x ({PART_LAB} labeled + {PART_UNL} unlabeled), {PART_BUDGET} picks each), {world} GPU"),
+        "scaling": "strong" if world > 1 else None, "partitions": PART_P, "partitions_on_busiest_rank": nmax,
+        "exchange": "none inside the loop: partition i runs on rank i % G, one gather of the picks" if world > 1 else None,
+        "dim": dim, "candidates": PART_P * PART_UNL, "labeled": PART_P * PART_LAB, "budget": PART_P * PART_BUDGET,
+        "value": PART_P * PART_UNL / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "picks_unique": unique,
+        "picks_match_single_gpu": match, "breakdown_ms": acc, "us_per_selection_step": step_ms * 1e3, "loop_variant": out.get("variant"),
+        "roofline": {"kernel": "greedy_persist_kernel, partitions as CTA groups of one launch", "bound": "hbm (L2 when a rank's rows fit the 126 MB L2)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "bytes_per_row_per_step": row_bytes,
+                     "rows_streamed_per_step_on_busiest_rank": nmax * PART_UNL,
+                     "note": "a fraction above 1 means the busiest rank's rows (8 000 x 8 KB per partition) are served from L2"},
     }
 
 
@@ -594,10 +742,9 @@ def run_own(args):
             with torch.cuda.stream(streams[k]):
                 if pair is not None:
                     pair[0].record()
-                e.score_softmax(logits, MODE_MARGIN, out=sc)
+                _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)   # K1 + K1b: ONE cooperative launch
                 if pair is not None:
                     pair[1].record()
-                pos = e.select_smallest(sc, BUDGET)
                 if group is None:
                     host_out[i & 1].copy_(pos, non_blocking=True)
                 else:
@@ -646,8 +793,7 @@ def run_own(args):
         for _ in range(5):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            eng.score_softmax(logits, MODE_MARGIN, out=scores)
-            pos = eng.select_smallest(scores, BUDGET)
+            _, pos = eng.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=scores)
             host_out[0].copy_(pos, non_blocking=True)
             torch.cuda.synchronize()
             lat.append(time.perf_counter() - t0)
@@ -693,7 +839,9 @@ def run_own(args):
         "host_enqueue_ms_per_step": (t_enq - t_w0) * 1e3 / args.steps,
         "latency_ms_single_query": latency_ms,
         "pipelined": pipelined,
-        "roofline": {"kernel": "rows_pipe_kernel<8,margin> (K1: TMA bulk-copy pipelined softmax-margin score)", "bound": "hbm",
+        "roofline": {"kernel": "rows_pipe_kernel<8,margin> with the fused selection epilogue (K1 + K1b in one cooperative launch: TMA bulk-copy "
+                               "pipelined softmax-margin score, then histogram / candidate / rank-by-counting stages behind two grid barriers); "
+                               "the CUDA events bracket the WHOLE kernel, selection included", "bound": "hbm",
                      "achieved": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9 / peak,
                      "traffic": ncu_traffic("score_margin"), "kernel_ms": k1_ms, "peak_source": peak_src,
@@ -725,6 +873,12 @@ def run_own(args):
             except Exception as exc:  # report, never hide
                 extras[kind] = {"error": repr(exc)}
             torch.cuda.empty_cache()
+        for kind in ("partitioned_coreset", "partitioned_badge"):
+            try:
+                extras[kind] = run_partitioned_workload(eng, kind, peak, steps=args.extra_steps, warmup=1, world=world, rank=rank)
+            except Exception as exc:  # report, never hide
+                extras[kind] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
         try:
             extras["mase_base"] = run_mase_workload(eng, peak, steps=args.extra_steps, warmup=1, rank=rank)
         except Exception as exc:  # report, never hide
@@ -733,9 +887,13 @@ def run_own(args):
         if world == 1:
             try:
                 cpu = cpu_greedy_baseline()
+                for kind, key in (("partitioned_coreset", "coreset"), ("partitioned_badge", "badge")):     # like for like
+                    if "error" not in extras.get(kind, {"error": 1}):
+                        extras[kind]["cpu_baseline"] = dict({k: v for k, v in cpu.items() if k not in ("coreset", "badge")}, **cpu[key])
                 for kind in ("coreset", "badge"):
                     if "error" not in extras.get(kind, {"error": 1}):
-                        extras[kind]["cpu_baseline"] = dict({k: v for k, v in cpu.items() if k not in ("coreset", "badge")}, **cpu[kind])
+                        extras[kind]["cpu_baseline"] = {"value": None, "note": "the reference cannot run the non-partitioned 130 000-row query "
+                                                        "(67.6 GB distance matrix); its like-for-like configuration is workloads.partitioned_*"}
             except Exception as exc:  # report, never hide
                 extras["cpu_greedy_baseline_error"] = repr(exc)
             try:

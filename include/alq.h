@@ -80,6 +80,14 @@ int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, i
 int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
                         int32_t* out_pos, void* stream);
 
+/* K1 + K1b as ONE launch: scores[i] as alq_score_softmax AND out_pos[0..b) as alq_select_smallest of those scores --
+ * the whole tail of MarginSampler.query / ConfidenceSampler.query (margin_sampler.py:33-42) behind one call.  When the
+ * pipelined scoring kernel applies (c % 4 == 0, contiguous rows, 4096 <= n <= ~240 000 per GPU) the selection runs in
+ * that kernel's epilogue (cooperative launch: per-CTA key lists in shared memory, one global 2048-bin histogram, the
+ * winners ranked by counting); otherwise the two kernels run back to back.  Same results either way.             */
+int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
+                         int64_t b, float* scores, int32_t* out_pos, void* stream);
+
 /* Multi-GPU top-B (rows sharded over G ranks): each rank packs its local winners as
  * out[i] = ord(scores[pos[i]]) << 32 | (row_lo + pos[i])  (i < k; padded with ~0 up to b_pad),
  * the G*b_pad words are all-gathered by the caller (NCCL), and alq_topb_merge returns the global

@@ -58,6 +58,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned 
 struct alq_ctx {
     int device = 0;
     int sm_count = 148;
+    int clock_khz = 1900000;              // SM clock (cached: the attribute query costs about a millisecond)
     size_t smem_optin = 0;
     cudaStream_t side_stream = nullptr;   // H2D pipelining for the *_host entry points
     cudaStream_t side_stream2 = nullptr;

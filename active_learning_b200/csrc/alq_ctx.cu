@@ -27,6 +27,7 @@ extern "C" int alq_create(alq_ctx** out, int device) {
         return ALQ_ERR_CUDA;  // built for sm_100a only
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if (prop.clockRate > 0) ctx->clock_khz = prop.clockRate;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking);

@@ -1153,8 +1153,7 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     ctx->comm.epoch += 1;
     A.ready_tag = ctx->comm.epoch << 32;
     A.tag_base = static_cast<unsigned int>(ctx->comm.epoch & 0x7fu) << 24 | 0x80000000u;   // never 0: a zeroed word is invalid
-    int clock_khz = 1900000;
-    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, ctx->device);
+    const int clock_khz = ctx->clock_khz;
     A.timeout_cycles = static_cast<long long>(ctx->spin_timeout_ms) * clock_khz;
     A.fast_path = ctx->d2_fast_path;
     if (const char* e = getenv("ALQ_D2_FAST_PATH")) A.fast_path = atoi(e) != 0;

@@ -113,7 +113,7 @@ __device__ __forceinline__ unsigned int ll_wait(const void* p, unsigned int tag,
 // (1) one warp spins on 32 sentinel words spread over the range -- one load per lane per round -- and only when
 // those have arrived (2) every poller loads its up-to-kBatch words as one batch (one L2 round trip), re-loading just
 // the few still missing.  Called by every consumer thread; the caller follows it with cons_bar().
-constexpr int kPollers = 256;
+constexpr int kPollers = 320;
 constexpr int kBatch = 8;
 template <typename Sink>
 __device__ __forceinline__ void ll_gather(const char* base, int nwords, int stride, unsigned long long tag, int shift,
@@ -234,6 +234,38 @@ __device__ __forceinline__ void block_locate(int n, int ct, int cw, int lane, do
     for (int w = 0; w < kConsWarps; ++w)
         if (idx < 0 && sh_hw[w] >= 0) { idx = sh_hw[w]; base = sh_bw[w]; }
     cons_bar();                               // sh_* are reused by the next call
+}
+
+// block_locate by ONE warp (n <= 2048 items): no block barrier, one shuffle scan.  Same contract.
+template <typename Mass>
+__device__ __forceinline__ void warp_locate(int n, int lane, double u_hi, double base0, double total_in, Mass mass,
+                                            int& idx, double& base, double& sum) {
+    const int per = (n + 31) / 32;
+    const int i0 = min(n, lane * per), i1 = min(n, i0 + per);
+    double loc = 0.0;
+    for (int i = i0; i < i1; ++i) loc += mass(i);
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double w = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += w;
+    }
+    sum = __shfl_sync(0xffffffffu, inc, 31);
+    const double total = total_in < 0.0 ? sum : total_in;
+    const double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    double run = base0 + (lane ? prev : 0.0);
+    int hit = -1;
+    double hb = 0.0;
+    const double thr = u_hi * total, thr_lo = thr * (1.0 - 8e-16), thr_hi = thr * (1.0 + 8e-16);   // see block_locate
+    for (int i = i0; i < i1; ++i) {
+        const double before = run, m = mass(i);
+        run += m;
+        if (hit < 0 && m > 0.0 && run > thr_lo && (run > thr_hi || (run / total) > u_hi)) { hit = i; hb = before; }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit >= 0);
+    const int src = bal ? __ffs(bal) - 1 : 0;
+    idx = bal ? __shfl_sync(0xffffffffu, hit, src) : -1;
+    base = __shfl_sync(0xffffffffu, hb, src);
 }
 
 // The exact D^2 draw, NumPy operation for operation (coreset_sampler.py:84-92): leaf sums of the float32 pairwise
@@ -461,7 +493,7 @@ __device__ __noinline__ int exact_draw(const PersistArgs& A, const PGroup* Gp, S
 
 template <bool FACTORED, bool SAMPLE>
 __global__ void __launch_bounds__(32 * (1 + kConsWarps), 1)
-greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, const int k_max, const int lc_max, const int ne_max) {
+greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, const int k_max, const int lc_max, const int ne_max, const int rm_max) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int d = A.d, c = FACTORED ? A.c : 0;
     const int dv = d >> 2, cv = c >> 2;
@@ -474,6 +506,7 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
     unsigned int* s_sched = reinterpret_cast<unsigned int*>(val + 2 * static_cast<size_t>(k_max));   // [k_max]
     int* s_rows = reinterpret_cast<int*>(s_sched + k_max);                                    // [lc_max * 128] row of each owned position
     double* s_u = reinterpret_cast<double*>(s_rows + static_cast<size_t>(lc_max) * 128);        // [ne_max] per-CTA masses of every rank (SAMPLE)
+    float* s_m = reinterpret_cast<float*>(s_u + ne_max);                                        // [rm_max] clip(mind, 0) of this CTA's rows (0: not kept)
     __shared__ SelShared ss;
 
     const BlockSeg seg = A.segs[blockIdx.x];
@@ -608,6 +641,7 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
                 if (SAMPLE) {
                     ll_store(valw + A.vpos[row], vtag, __float_as_uint(m));
                     usum += static_cast<double>(fmaxf(m, 0.f));
+                    if (rm_max) s_m[row - seg.row_lo] = fmaxf(m, 0.f);
                 } else {
                     const unsigned long long k = (static_cast<unsigned long long>(alq_ord(m)) << 32) | (0xffffffffu - static_cast<uint32_t>(row - seg.row_lo));
                     best_key = k > best_key ? k : best_key;
@@ -681,6 +715,7 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
                         if (SAMPLE) {
                             ll_store(valw + vp, vtag, __float_as_uint(m));   // raw running min (exact path); the draw clips at 0
                             usum += static_cast<double>(fmaxf(m, 0.f));
+                            if (rm_max) s_m[row - seg.row_lo] = fmaxf(m, 0.f);
                         } else {
                             const unsigned long long k = (static_cast<unsigned long long>(alq_ord(m)) << 32) | (0xffffffffu - static_cast<uint32_t>(row - seg.row_lo));
                             best_key = k > best_key ? k : best_key;
@@ -735,6 +770,7 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
         } else {
             if (prof) ss.prof[8] = gtime_ns();
             if (dbg && t == dbg_step) dbg[0] = gtime_ns();
+            if (dbg && t == dbg_step + 9) { dbg[3] = gtime_ns(); unsigned int sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[4] = sm; }
             // ================= certified fast path =================
             // np.random.choice picks the first k with cdf[k] > u, cdf = cumsum64(fl32(c / S)) / its last entry.  Every
             // fl32(c_i / S) is c_i / S (1 + e_i), |e_i| <= 2^-24 (or an absolute 2^-150 when it underflows), and S cancels
@@ -780,7 +816,17 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
                 if (dbg && t == dbg_step) dbg[1] = gtime_ns();
                 int e_hit;
                 double e_base, q_tot;
-                block_locate(ne, ct, cw, lane, u + kMargin, 0.0, -1.0, [&](int i) { return s_u[i]; }, ss.w, ss.hw, ss.bw, e_hit, e_base, q_tot);
+                if (ne <= 2048) {             // one warp, no block barriers
+                    if (cw == 0) {
+                        warp_locate(ne, lane, u + kMargin, 0.0, -1.0, [&](int i) { return s_u[i]; }, e_hit, e_base, q_tot);
+                        if (lane == 0) { ss.hw[0] = e_hit; ss.bw[0] = e_base; ss.w[0] = q_tot; }
+                    }
+                    cons_bar();
+                    e_hit = ss.hw[0]; e_base = ss.bw[0]; q_tot = ss.w[0];
+                    cons_bar();
+                } else {
+                    block_locate(ne, ct, cw, lane, u + kMargin, 0.0, -1.0, [&](int i) { return s_u[i]; }, ss.w, ss.hw, ss.bw, e_hit, e_base, q_tot);
+                }
                 const bool sane = q_tot > 0.0 && q_tot <= 1.0e300;
                 if (!sane || e_hit < 0 || !((e_base / q_tot) <= u - kMargin)) exact = true;     // same verdict in every CTA of every rank
                 if (dbg && t == dbg_step) dbg[2] = gtime_ns();
@@ -788,14 +834,25 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
                     const unsigned int ptag = A.tag_base | (++rnd_pick & 0xffffffu);
                     const unsigned int pslot = rnd_pick & 1u;
                     if (e_hit == A.rank * stride + grank) {       // the crossing is inside this CTA's rows
-                        int r_hit;
-                        double r_base, r_sum;
-                        block_locate(nrows, ct, cw, lane, u + kMargin, e_base, q_tot,
-                                     [&](int i) { return static_cast<double>(fmaxf(__ldcg(A.mind + seg.row_lo + i), 0.f)); },
-                                     ss.w, ss.hw, ss.bw, r_hit, r_base, r_sum);
-                        unsigned int word = 0xffffffffu;          // "not certain": everybody takes the exact path
-                        if (r_hit >= 0 && (r_base / q_tot) <= u - kMargin) word = static_cast<unsigned int>(seg.row_lo + r_hit);
-                        if (ct < A.world) ll_store(A.peer[ct] + G.pickw + pslot * 8, ptag, word);
+                        int r_hit = -1;
+                        double r_base = 0.0, r_sum;
+                        if (nrows <= 2048) {                      // one warp; the rows' masses are in shared memory if kept
+                            if (cw == 0) {
+                                if (rm_max) warp_locate(nrows, lane, u + kMargin, e_base, q_tot, [&](int i) { return static_cast<double>(s_m[i]); }, r_hit, r_base, r_sum);
+                                else warp_locate(nrows, lane, u + kMargin, e_base, q_tot,
+                                                 [&](int i) { return static_cast<double>(fmaxf(__ldcg(A.mind + seg.row_lo + i), 0.f)); }, r_hit, r_base, r_sum);
+                                unsigned int word = 0xffffffffu;  // "not certain": everybody takes the exact path
+                                if (r_hit >= 0 && (r_base / q_tot) <= u - kMargin) word = static_cast<unsigned int>(seg.row_lo + r_hit);
+                                if (lane < A.world) ll_store(A.peer[lane] + G.pickw + pslot * 8, ptag, word);
+                            }
+                        } else {
+                            block_locate(nrows, ct, cw, lane, u + kMargin, e_base, q_tot,
+                                         [&](int i) { return static_cast<double>(fmaxf(__ldcg(A.mind + seg.row_lo + i), 0.f)); },
+                                         ss.w, ss.hw, ss.bw, r_hit, r_base, r_sum);
+                            unsigned int word = 0xffffffffu;
+                            if (r_hit >= 0 && (r_base / q_tot) <= u - kMargin) word = static_cast<unsigned int>(seg.row_lo + r_hit);
+                            if (ct < A.world) ll_store(A.peer[ct] + G.pickw + pslot * 8, ptag, word);
+                        }
                         if (dbg && t == dbg_step && ct == 0) dbg[6] = gtime_ns();
                     }
                     if (ct == 0) ss.centre = static_cast<int>(ll_wait(win + G.pickw + pslot * 8, ptag, A));
@@ -866,11 +923,11 @@ struct PairTree {
 };
 
 template <bool FACTORED, bool SAMPLE>
-cudaError_t launch_persist(int grid, size_t smem, cudaStream_t st, PersistArgs& A, PipeCfg& cfg, int& k_max, int& lc_max, int& ne_max) {
+cudaError_t launch_persist(int grid, size_t smem, cudaStream_t st, PersistArgs& A, PipeCfg& cfg, int& k_max, int& lc_max, int& ne_max, int& rm_max) {
     auto* fn = greedy_persist_kernel<FACTORED, SAMPLE>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    void* args[] = {&A, &cfg, &k_max, &lc_max, &ne_max};
+    void* args[] = {&A, &cfg, &k_max, &lc_max, &ne_max, &rm_max};
     return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fn), dim3(grid), dim3(32 * (1 + kConsWarps)), args, smem, st);
 }
 
@@ -1043,11 +1100,14 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     // ---- shared-memory plan: centre + ring + tree ---------------------------------------------------------
     PipeCfg cfg{};
     size_t smem = 0;
-    int ne_max = 1;
+    int ne_max = 1, rm_max = 0;
     {
+        int seg_rows = 0;
+        for (const BlockSeg& sg : segs) seg_rows = std::max(seg_rows, sg.row_hi - sg.row_lo);
+        if (sample && seg_rows <= 2048) rm_max = (seg_rows + 3) & ~3;      // clip(mind, 0) of a CTA's rows stays in shared memory
         const size_t centre_bytes = static_cast<size_t>((d + c + 31) & ~31) * 4;
         for (int p = 0; p < P; ++p) ne_max = std::max(ne_max, world * groups[p].seg_stride);
-        const size_t tree_bytes = (sample ? static_cast<size_t>(k_max) * 12 + static_cast<size_t>(lc_max) * 512 + 64 : 64 + 12 + 512) + static_cast<size_t>(ne_max) * 8;
+        const size_t tree_bytes = (sample ? static_cast<size_t>(k_max) * 12 + static_cast<size_t>(lc_max) * 512 + 64 : 64 + 12 + 512) + static_cast<size_t>(ne_max) * 8 + static_cast<size_t>(rm_max) * 4;
         const size_t fixed = centre_bytes + tree_bytes + kConsWarps * 16 + 256;
         const size_t budget_bytes = ctx->smem_optin > 8192 ? ctx->smem_optin - 1536 : 0;
         size_t tile_target = 32 * 1024;
@@ -1163,8 +1223,8 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         ALQ_LAUNCH_CHECK(ctx);
     }
     cudaError_t le;
-    if (factored) le = sample ? launch_persist<true, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max) : launch_persist<true, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max);
-    else le = sample ? launch_persist<false, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max) : launch_persist<false, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max);
+    if (factored) le = sample ? launch_persist<true, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max) : launch_persist<true, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max);
+    else le = sample ? launch_persist<false, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max) : launch_persist<false, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max);
     if (le != cudaSuccess) {
         cudaGetLastError();
         ALQ_FAIL(ctx, ALQ_ERR_CUDA, "alq_greedy_select: cooperative launch failed: %s (grid %d, %zu B shared)", cudaGetErrorString(le), grid, smem);
@@ -1204,8 +1264,18 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
                 const unsigned long long v = h[8 * b + k] - t0;
                 mn = std::min(mn, v); mx = std::max(mx, v); mean += v; ++cnt;
             }
+            if (k == 3 || k == 4) continue;
             if (cnt) fprintf(stderr, "[alq persist dbg] %-20s min %7.2f mean %7.2f max %7.2f us (%d CTAs) after the first CTA's stream end\n", names[k], mn * 1e-3, mean / cnt * 1e-3, mx * 1e-3, cnt);
         }
+    }
+    if (D->step_kernel_ms_host && getenv("ALQ_PERSIST_DEBUG") && atoi(getenv("ALQ_PERSIST_DEBUG")) >= 2) {
+        std::vector<unsigned long long> h(8 * static_cast<size_t>(grid));
+        cudaMemcpy(h.data(), d_prof + 8, h.size() * 8, cudaMemcpyDeviceToHost);
+        unsigned long long a0 = ~0ull, b0 = ~0ull;
+        for (int b = 0; b < grid; ++b) { if (h[8 * b]) a0 = std::min(a0, h[8 * b]); if (h[8 * b + 3]) b0 = std::min(b0, h[8 * b + 3]); }
+        fprintf(stderr, "[alq persist skew] cta smid lateness_us(step A) lateness_us(step A+9)\n");
+        for (int b = 0; b < grid; ++b)
+            fprintf(stderr, "[alq persist skew] %d %llu %.2f %.2f\n", b, h[8 * b + 4], (h[8 * b] - a0) * 1e-3, (h[8 * b + 3] - b0) * 1e-3);
     }
     if (status == ALQ_ERR_STATE) ALQ_FAIL(ctx, status, "alq_greedy_select: timed out waiting for a peer GPU (or a CTA of this grid)");
     if (status != 0) ALQ_FAIL(ctx, status, "alq_greedy_select: non-finite or empty probability mass during D^2 sampling");

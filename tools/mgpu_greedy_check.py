@@ -82,11 +82,12 @@ def case(n, l, d, c, b, ints, seed, uneven=False):
         ok = ok and bool(allsame.item())
 
 
-case(6001, 700, 512, 0, 64, True, 1)
-case(6001, 700, 512, 40, 64, True, 2, uneven=True)
-case(3000, 300, 2048, 0, 40, False, 3)
-case(3000, 300, 2048, 1000, 40, False, 4)
-if len(sys.argv) > 1 and sys.argv[1] == "big":
+if not (len(sys.argv) > 1 and sys.argv[1] == "bigonly"):
+    case(6001, 700, 512, 0, 64, True, 1)
+    case(6001, 700, 512, 40, 64, True, 2, uneven=True)
+    case(3000, 300, 2048, 0, 40, False, 3)
+    case(3000, 300, 2048, 1000, 40, False, 4)
+if len(sys.argv) > 1 and sys.argv[1] in ("big", "bigonly"):
     case(80000, 50000, 2048, 0, 2000, False, 5)
     case(80000, 50000, 2048, 1000, 2000, False, 6)
 dist.barrier()

@@ -13,7 +13,7 @@ from active_learning_b200.engine import Engine  # noqa: E402
 eng = Engine(0)
 dev = eng.device
 g = torch.Generator(device=dev).manual_seed(0)
-N, C, D, L = 80000, 1000, 2048, 50000
+N, C, D, L = int(os.environ.get("PT_ROWS", "80000")), 1000, 2048, 50000
 B = int(os.environ.get("PT_STEPS", "1000"))
 variants = [int(v) for v in os.environ.get("PT_VARIANTS", "2,3").split(",")]
 kinds = os.environ.get("PT_KINDS", "dense,factored").split(",")

@@ -28,7 +28,11 @@ struct AlqComm {            // peer-memory group (alq_comm.cu)
     // tail of the window reserved for the top-B exchange (alq_topb_exchange): 2 parities x world lists + flags
     static constexpr size_t kTopbWords = 16384;
     size_t topb_region_bytes() const { return 2 * (static_cast<size_t>(world) * kTopbWords * 8 + 1024); }
-    size_t greedy_bytes() const { return bytes > topb_region_bytes() ? bytes - topb_region_bytes() : 0; }
+    // ... and, in front of it, the regions of the fused multi-GPU tail (alq_uncertainty_tail_sharded): 2 parities x
+    // {histogram words, per-CTA counts, candidate words}
+    static constexpr size_t kTailRegionBytes = 6u << 20;
+    size_t tail_region_off() const { return bytes - topb_region_bytes() - kTailRegionBytes; }
+    size_t greedy_bytes() const { return bytes > topb_region_bytes() + kTailRegionBytes ? bytes - topb_region_bytes() - kTailRegionBytes : 0; }
 };
 
 // system-scope flag helpers shared by the multi-GPU kernels

@@ -168,6 +168,19 @@ struct SelArgs {
     unsigned long long* g_cand;     // [n]
     int32_t* out_pos;               // [b]
     long long* dbg;                 // optional phase stamps of CTA 0 (ALQ_SELECT_DEBUG)
+    // rows sharded over `world` GPUs (0 / 1: single GPU): the histograms are summed and the candidates gathered through
+    // the peer-memory windows from inside this kernel, every rank ends with the same global list
+    int world, rank;
+    unsigned int row_base;          // global position of this rank's row 0
+    char* peer[ALQ_MAX_WORLD];
+    unsigned long long hist_off;    // u64 LL words [2 levels][world][2048]   {tag32, count32}
+    unsigned long long cnt_off;     // u64 LL words [world][stride]            {tag32, candidates of that CTA}
+    unsigned long long cand_off;    // u64 raw words [world][cand_cap]
+    int stride, cand_cap;
+    unsigned int tag;               // 0x80000000 | call epoch
+    long long timeout_cycles;
+    int* status;                    // mapped host word (sticky)
+    unsigned int* g_tot;            // [2 * 2048] histograms summed over the ranks (local)
 };
 
 __device__ __forceinline__ void sel_grid_barrier(unsigned int* ctr, unsigned int target) {
@@ -371,6 +384,197 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
     if (dbg) { dbg[5] = clock64(); dbg[6] = total; dbg[7] = nc; }
 }
 
+__device__ __forceinline__ void sel_ll_store(void* p, unsigned int tag, unsigned int payload) {
+    const unsigned long long v = (static_cast<unsigned long long>(tag) << 32) | payload;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int sel_ll_wait(const void* p, unsigned int tag, const SelArgs& S) {
+    unsigned long long v;
+    const long long t0 = clock64();
+    for (int spin = 0;; ++spin) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (static_cast<unsigned int>(v >> 32) == tag) break;
+        if ((spin & 63) == 63 && (*reinterpret_cast<volatile int*>(S.status) != 0 || clock64() - t0 > S.timeout_cycles)) {
+            *reinterpret_cast<volatile int*>(S.status) = ALQ_ERR_STATE;
+            __threadfence_system();
+            break;
+        }
+    }
+    return static_cast<unsigned int>(v);
+}
+
+// The same selection with the rows sharded over `world` GPUs: K1 + K1b + the exchange in ONE launch per rank.  Both
+// histogram levels are summed over the ranks (every CTA publishes a slice of its rank's bins to every window as LL
+// words and sums the same slice of all ranks), so every rank finds the same 22-bit threshold; the candidates (b + a few
+// words over ALL ranks, not b per rank) are stored into every window, each CTA's count follows behind a system fence
+// as an LL word; then every rank ranks the whole list (CTA c takes slice c) -- all ranks end with the same out_pos.
+__device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_hist, unsigned long long* s_list, int* s_misc,
+                                                  unsigned long long* buf, int buf_cap) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int grid = gridDim.x, W = S.world;
+    char* const win = S.peer[S.rank];
+    long long* dbg = (S.dbg && blockIdx.x == 0 && tid == 0) ? S.dbg : nullptr;
+    __syncthreads();
+    if (dbg) dbg[0] = clock64();
+    const int cnt = s_misc[0];
+    uint32_t want = static_cast<uint32_t>(S.b), T0 = 0;
+    const int per = (2048 + grid - 1) / grid, b_lo = min(2048, static_cast<int>(blockIdx.x) * per), b_hi = min(2048, b_lo + per);
+    for (int level = 0; level < 2; ++level) {
+        if (level == 1) {
+            for (int i = tid; i < 2048; i += nthr) s_hist[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < cnt; i += nthr) {
+                const uint32_t key = static_cast<uint32_t>(s_list[i] >> 32);
+                if ((key >> 21) == T0) atomicAdd(&s_hist[(key >> 10) & 0x7ffu], 1u);
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < 2048; i += nthr) {
+            const uint32_t h = s_hist[i];
+            if (h) atomicAdd(S.g_hist + level * 2048 + i, h);
+        }
+        sel_grid_barrier(S.g_ctr, static_cast<unsigned int>(2 * level + 1) * grid);
+        // this CTA's slice of the rank histogram -> every rank; then the same slice summed over the ranks
+        for (int i = tid; i < (b_hi - b_lo) * W; i += nthr) {
+            const int bin = b_lo + i / W, p = i % W;
+            sel_ll_store(S.peer[p] + S.hist_off + (static_cast<size_t>(level * W + S.rank) * 2048 + bin) * 8, S.tag,
+                         __ldcg(S.g_hist + level * 2048 + bin));
+        }
+        for (int i = tid; i < (b_hi - b_lo); i += nthr) {
+            uint32_t sum = 0;
+            for (int r = 0; r < W; ++r)
+                sum += sel_ll_wait(win + S.hist_off + (static_cast<size_t>(level * W + r) * 2048 + b_lo + i) * 8, S.tag, S);
+            S.g_tot[level * 2048 + b_lo + i] = sum;
+        }
+        sel_grid_barrier(S.g_ctr, static_cast<unsigned int>(2 * level + 2) * grid);
+        {
+            uint32_t hv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hv[k] = (tid + k * nthr) < 2048 ? __ldcg(S.g_tot + level * 2048 + tid + k * nthr) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((tid + k * nthr) < 2048) s_hist[tid + k * nthr] = hv[k];
+        }
+        __syncthreads();
+        sel_find_bin(s_hist, want, reinterpret_cast<uint32_t*>(s_misc + 16), &s_misc[level == 0 ? 1 : 5], &s_misc[2]);
+        want = static_cast<uint32_t>(s_misc[2]);
+        if (level == 0) T0 = static_cast<uint32_t>(s_misc[1]);
+        __syncthreads();
+    }
+    const uint32_t T = (T0 << 11) | static_cast<uint32_t>(s_misc[5]);
+    if (tid == 0) s_misc[4] = 0;
+    __syncthreads();
+    if (dbg) dbg[1] = clock64();
+    // ---- this CTA's candidates -> the rank's region of every window; the count follows behind a system fence ----
+    for (int i = tid; i < cnt; i += nthr) {
+        const unsigned long long w = s_list[i];
+        if (static_cast<uint32_t>(w >> 42) <= T) buf[atomicAdd(&s_misc[4], 1)] = w;
+    }
+    __syncthreads();
+    const int nc = s_misc[4];
+    if (tid == 0) s_misc[3] = static_cast<int>(atomicAdd(S.g_ctr + 1, static_cast<unsigned int>(nc)));
+    __syncthreads();
+    const int off = s_misc[3];
+    if (off + nc > S.cand_cap && tid == 0) { *reinterpret_cast<volatile int*>(S.status) = ALQ_ERR_STATE; __threadfence_system(); }
+    for (int i = tid; i < nc * W; i += nthr) {
+        const int k = i / W, p = i % W;
+        if (off + k < S.cand_cap)
+            reinterpret_cast<unsigned long long*>(S.peer[p] + S.cand_off)[static_cast<size_t>(S.rank) * S.cand_cap + off + k] = buf[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();               // the candidate words are visible in every window before the count is
+        for (int p = 0; p < W; ++p)
+            sel_ll_store(S.peer[p] + S.cnt_off + (static_cast<size_t>(S.rank) * S.stride + blockIdx.x) * 8, S.tag, static_cast<unsigned int>(nc));
+    }
+    // ---- counts of every CTA of every rank -> per-rank totals ----
+    uint32_t* s_tot = reinterpret_cast<uint32_t*>(s_misc + 24);      // [8]
+    if (tid < ALQ_MAX_WORLD) s_tot[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < W * S.stride; i += nthr) {
+        const int r = i / S.stride;
+        const uint32_t v = sel_ll_wait(win + S.cnt_off + static_cast<size_t>(i) * 8, S.tag, S);
+        if (v) atomicAdd(&s_tot[r], v);
+    }
+    __syncthreads();
+    if (dbg) dbg[2] = clock64();
+    // ---- the whole list into shared memory: one bulk copy per rank segment (segments padded to an even word count) ----
+    int seg_off[ALQ_MAX_WORLD + 1];
+    seg_off[0] = 0;
+    for (int r = 0; r < W; ++r) seg_off[r + 1] = seg_off[r] + static_cast<int>((min(s_tot[r], static_cast<uint32_t>(S.cand_cap)) + 1u) & ~1u);
+    const int M = seg_off[W];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_misc + 8);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (M > buf_cap) {                        // does not fit (the host sizes the buffer for b + slack): report, never guess
+        if (tid == 0) { *reinterpret_cast<volatile int*>(S.status) = ALQ_ERR_STATE; __threadfence_system(); }
+        return;
+    }
+    if (tid == 0 && M > 0) {
+        mbar_expect_tx(bar, static_cast<uint32_t>(M) * 8u);
+        for (int r = 0; r < W; ++r)
+            if (seg_off[r + 1] > seg_off[r])
+                bulk_g2s(buf + seg_off[r], win + S.cand_off + static_cast<size_t>(r) * S.cand_cap * 8,
+                         static_cast<uint32_t>(seg_off[r + 1] - seg_off[r]) * 8u, bar);
+    }
+    if (M > 0) mbar_wait(bar, 0);
+    if (tid < W && (s_tot[tid] & 1u)) buf[seg_off[tid] + s_tot[tid]] = ~0ull;       // the pad word sorts behind everything
+    __syncthreads();
+    if (dbg) dbg[3] = clock64();
+    // ---- CTA c ranks slice c of the list ----
+    const int perc = (M + grid - 1) / grid, s0 = min(M, static_cast<int>(blockIdx.x) * perc), n2 = min(M, s0 + perc) - s0;
+    {
+        unsigned long long* tmp = buf + buf_cap;            // [list_cap] words behind the chunk buffer
+        for (int i = tid; i < n2; i += nthr) {
+            const unsigned long long w = buf[s0 + i];
+            int r = 0;
+            for (int q = 0; q < n2; ++q) {
+                const unsigned long long x = buf[s0 + q];
+                r += (x < w) || (x == w && q < i);          // pads (equal ~0 words) keep distinct slots
+            }
+            tmp[r] = w;
+        }
+        __syncthreads();
+        for (int i = tid; i < n2; i += nthr) s_list[i] = tmp[i];
+    }
+    for (int i = tid; i <= n2; i += nthr) s_hist[i] = 0;
+    __syncthreads();
+    for (int j = tid; j < M; j += nthr) {
+        const unsigned long long x = buf[j];
+        int lo = 0, hi = n2;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_list[mid] <= x) lo = mid + 1; else hi = mid;
+        }
+        atomicAdd(&s_hist[lo], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t carry = 0;
+        for (int base = 0; base < n2; base += 32) {
+            const int i = base + lane;
+            uint32_t v = i < n2 ? s_hist[i] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (i < n2) s_hist[i] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n2; i += nthr) {
+        const uint32_t r = s_hist[i];
+        const unsigned long long w = s_list[i];
+        if (r < static_cast<uint32_t>(S.b) && w != ~0ull) S.out_pos[r] = static_cast<int32_t>(w & 0xffffffffu);
+    }
+    if (dbg) { dbg[4] = clock64(); dbg[5] = clock64(); dbg[6] = M; dbg[7] = n2; }
+}
+
 // MODE 0..2: scores; MODE 3: BADGE factors (writes a[row, :] and a_norm2[row]);
 // MODE 4: MASE minimum margin + predicted class (K6, table reads pruned); MODE 5: MASE with the per-class radii written
 constexpr int MODE_MASE_MIN = 4, MODE_MASE_FULL = 5;
@@ -499,15 +703,18 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
                 if (MODE >= MODE_MASE_MIN) mase.pred[row0 + lane] = my_pred;
                 if (sel.b > 0) {
                     const uint32_t key = alq_ord(my_score + 0.0f);
-                    s_list[atomicAdd(&s_misc[0], 1)] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(row0 + lane);
+                    s_list[atomicAdd(&s_misc[0], 1)] = (static_cast<unsigned long long>(key) << 32) | (sel.row_base + static_cast<uint32_t>(row0 + lane));
                     atomicAdd(&s_hist[key >> 21], 1u);
                 }
             }
         }
     }
-    if (sel.b > 0)       // every thread of the CTA (the tile ring is free now: it becomes the candidate buffer)
-        select_epilogue(sel, s_hist, s_list, s_misc, reinterpret_cast<unsigned long long*>(tiles),
-                        sel.list_off / 8 - sel.list_cap - 2);
+    if (sel.b > 0) {     // every thread of the CTA (the tile ring is free now: it becomes the candidate buffer)
+        if (sel.world > 1) select_epilogue_mgpu(sel, s_hist, s_list, s_misc, reinterpret_cast<unsigned long long*>(tiles),
+                                                sel.list_off / 8 - sel.list_cap - 2);
+        else select_epilogue(sel, s_hist, s_list, s_misc, reinterpret_cast<unsigned long long*>(tiles),
+                             sel.list_off / 8 - sel.list_cap - 2);
+    }
 }
 
 // Any c / alignment: two passes over the row, the second one hits L1/L2.
@@ -851,7 +1058,7 @@ extern "C" int alq_score_softmax(alq_ctx* ctx, const float* logits, int64_t n, i
 
 // zeroed scratch of one fused launch (2048-bin histogram + counters): slots of a ring cleared in bulk
 static unsigned int* next_sel_slot(alq_ctx* ctx, cudaStream_t st) {
-    constexpr int kSlots = 64, kWords = 2 * 2048 + 16;
+    constexpr int kSlots = 64, kWords = 4 * 2048 + 16;      // 2 level histograms, their cross-rank sums, counters
     if (!ctx->sel_ring) {
         if (cudaMalloc(&ctx->sel_ring, static_cast<size_t>(kSlots) * kWords * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         cudaMemset(ctx->sel_ring, 0, static_cast<size_t>(kSlots) * kWords * 4);
@@ -864,36 +1071,63 @@ static unsigned int* next_sel_slot(alq_ctx* ctx, cudaStream_t st) {
     return ctx->sel_ring + static_cast<size_t>(ctx->sel_ring_next++) * kWords;
 }
 
-extern "C" int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
-                                    int64_t b, float* scores, int32_t* out_pos, void* stream) {
+// shared implementation: world_rows == nullptr -> single GPU
+static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
+                                 int64_t b, float* scores, int32_t* out_pos, void* stream, bool sharded, int64_t row_lo,
+                                 int64_t rows_min, int64_t rows_max) {
     if (!ctx) return ALQ_ERR_INVALID;
-    if (n < 0 || c <= 0 || ld < c || mode < 0 || mode > 2 || b < 0 || b > n)
+    if (n < 0 || c <= 0 || ld < c || mode < 0 || mode > 2 || b < 0 || (!sharded && b > n))
         ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_tail: bad shape n=%lld c=%d ld=%lld mode=%d b=%lld", (long long)n, c,
                  (long long)ld, mode, (long long)b);
-    if (n == 0 || b == 0) return ALQ_OK;
+    if ((!sharded && n == 0) || b == 0) return ALQ_OK;
     if (!logits || !scores || !out_pos) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_tail: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AlqComm& G = ctx->comm;
+    if (sharded && (G.world <= 1 || !G.connected)) ALQ_FAIL(ctx, ALQ_ERR_STATE, "alq_uncertainty_tail_sharded: no multi-GPU group (alq_comm_create/connect)");
+    if (!sharded) { rows_min = rows_max = n; }
     constexpr int kListCap = 2048;
     const size_t reserve = static_cast<size_t>(kListCap) * 8 + 2064 * 4 + 256;
     RowPipeCfg cfg{};
     size_t smem = 0;
     const bool vec = (c % 4 == 0) && (ld == c) && aligned16(logits) && c <= 2048;
-    const bool fused = vec && n >= 4096 && n < (1LL << 31) && ctx->select_impl != 1 && ctx->greedy_variant != 1 &&
-                       n * 5 <= static_cast<int64_t>(ctx->sm_count) * kListCap * 4 &&       // the per-CTA lists absorb any imbalance
-                       plan_row_pipe(ctx, c, cfg, smem, reserve);
-    if (!fused) {                                   // two launches: K1 then K1b
+    // every rank must take the same path: the decision only uses what all ranks know (c, b, the smallest and largest shard)
+    bool fused = vec && rows_min >= 4096 && rows_max < (1LL << 31) && ctx->select_impl != 1 && ctx->greedy_variant != 1 &&
+                 rows_max * 5 <= static_cast<int64_t>(ctx->sm_count) * kListCap * 4 &&     // the per-CTA lists absorb any imbalance
+                 plan_row_pipe(ctx, c, cfg, smem, reserve);
+    if (fused && sharded) {
+        const int64_t tiles_min = (rows_min + cfg.rows_per_tile - 1) / cfg.rows_per_tile;
+        const size_t need = 2 * (static_cast<size_t>(2) * G.world * 2048 * 8 + static_cast<size_t>(G.world) * ctx->sm_count * 8 +
+                                 static_cast<size_t>(G.world) * (b + 4096) * 8 + 1024);
+        fused = tiles_min >= ctx->sm_count && b + 2 * G.world + 64 <= 14000 && need <= AlqComm::kTailRegionBytes &&
+                G.bytes > G.topb_region_bytes() + AlqComm::kTailRegionBytes && ctx->xchg_status_dev != nullptr;
+    }
+    if (!fused) {                                   // separate launches: K1, K1b (and the window exchange of the local winners)
         int rc = alq_score_softmax(ctx, logits, n, c, ld, mode, scores, stream);
         if (rc) return rc;
-        return alq_select_smallest(ctx, scores, n, b, out_pos, stream);
+        if (!sharded) return alq_select_smallest(ctx, scores, n, b, out_pos, stream);
+        const int64_t k = std::min<int64_t>(b, n);
+        rc = alq_scratch_reserve(ctx, scratch_need({static_cast<size_t>(n) * 8 + 16, static_cast<size_t>(k + 1) * 4}));   // the selects below reuse the front
+        if (rc) return rc;
+        int32_t* pos_loc = nullptr;
+        if (cudaMallocAsync(reinterpret_cast<void**>(&pos_loc), static_cast<size_t>(k + 1) * 4, st) != cudaSuccess) {
+            cudaGetLastError();
+            ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_uncertainty_tail_sharded: allocation failed");
+        }
+        rc = k > 0 ? alq_select_smallest(ctx, scores, n, k, pos_loc, stream) : ALQ_OK;
+        if (!rc) rc = alq_topb_exchange(ctx, scores, pos_loc, k, row_lo, b, out_pos, stream);
+        cudaFreeAsync(pos_loc, st);
+        return rc;
     }
+    if (sharded)
+        if (int rc0 = alq_comm_check(ctx)) return rc0;       // a previous asynchronous exchange that timed out
     int rc = alq_scratch_reserve(ctx, scratch_need({static_cast<size_t>(n) * 8 + 16}));
     if (rc) return rc;
     SelArgs sel{};
     sel.b = static_cast<int>(b);
     sel.list_cap = kListCap;
-    {   // the pipe plan put `reserve` bytes behind the ring: the list starts there, but never below 80 KB + scratch
+    {   // the pipe plan put `reserve` bytes behind the ring: the list starts there, but never below 128 KB + scratch
         const size_t ring_end = (smem - reserve + 15) & ~size_t(15);
-        const size_t off = std::max<size_t>(ring_end, 80 * 1024 + static_cast<size_t>(kListCap) * 8);
+        const size_t off = std::max<size_t>(ring_end, 128 * 1024 + static_cast<size_t>(kListCap) * 8);
         sel.list_off = static_cast<int>(off);
         smem = off + reserve;
         if (smem > ctx->smem_optin) ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_tail: shared-memory plan does not fit");
@@ -901,7 +1135,8 @@ extern "C" int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n
     unsigned int* slot = next_sel_slot(ctx, st);
     if (!slot) ALQ_FAIL(ctx, ALQ_ERR_NOMEM, "alq_uncertainty_tail: scratch allocation failed");
     sel.g_hist = slot;
-    sel.g_ctr = slot + 2 * 2048;
+    sel.g_ctr = slot + 4 * 2048;
+    sel.g_tot = slot + 2 * 2048;
     static long long* dbg_buf = nullptr;
     if (getenv("ALQ_SELECT_DEBUG")) {
         if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
@@ -909,6 +1144,22 @@ extern "C" int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n
     }
     sel.g_cand = ScratchCursor(ctx->scratch).take<unsigned long long>(n + 2);
     sel.out_pos = out_pos;
+    if (sharded) {
+        G.epoch += 1;
+        sel.world = G.world; sel.rank = G.rank;
+        sel.row_base = static_cast<unsigned int>(row_lo);
+        for (int r = 0; r < G.world; ++r) sel.peer[r] = G.peer[r];
+        sel.stride = ctx->sm_count;
+        sel.cand_cap = static_cast<int>(b + 4096);
+        const size_t hist_bytes = static_cast<size_t>(2) * G.world * 2048 * 8, cnt_bytes = (static_cast<size_t>(G.world) * sel.stride * 8 + 127) & ~size_t(127);
+        const size_t base = G.tail_region_off() + (G.epoch & 1) * (AlqComm::kTailRegionBytes / 2);
+        sel.hist_off = base;
+        sel.cnt_off = base + hist_bytes;
+        sel.cand_off = sel.cnt_off + cnt_bytes;
+        sel.tag = 0x80000000u | static_cast<unsigned int>(G.epoch & 0x7fffffffu);
+        sel.timeout_cycles = static_cast<long long>(ctx->spin_timeout_ms) * ctx->clock_khz;
+        sel.status = ctx->xchg_status_dev;
+    }
     cudaError_t e;
     if (mode == ALQ_MODE_MARGIN) e = launch_rows_pipe_nv<ALQ_MODE_MARGIN>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0, MaseArgs{}, sel);
     else if (mode == ALQ_MODE_LEAST_CONFIDENCE) e = launch_rows_pipe_nv<ALQ_MODE_LEAST_CONFIDENCE>(ctx, st, cfg, smem, logits, n, c, scores, 1, 0, n, nullptr, 0, MaseArgs{}, sel);
@@ -918,7 +1169,13 @@ extern "C" int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n
         cudaGetLastError();
         ALQ_FAIL(ctx, ALQ_ERR_CUDA, "alq_uncertainty_tail: cooperative launch failed: %s", cudaGetErrorString(e));
     }
-    if (sel.dbg) {
+    if (sel.dbg && sharded) {
+        long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, sel.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[alq fused tail dbg, rank %d] cycles: two summed histogram levels %lld, candidates + counts %lld, list load %lld, rank %lld | list %lld words, CTA 0 ranks %lld\n",
+                G.rank, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[6], h[7]);
+    } else if (sel.dbg) {
         long long h[8];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, sel.dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -926,6 +1183,22 @@ extern "C" int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n
                 h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6], h[7]);
     }
     return ALQ_OK;
+}
+
+extern "C" int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
+                                    int64_t b, float* scores, int32_t* out_pos, void* stream) {
+    return uncertainty_tail_impl(ctx, logits, n, c, ld, mode, b, scores, out_pos, stream, false, 0, n, n);
+}
+
+extern "C" int alq_uncertainty_tail_sharded(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
+                                            int64_t b, int64_t row_lo, int64_t rows_min, int64_t rows_max, float* scores,
+                                            int32_t* out_gpos, void* stream) {
+    if (rows_min < 0 || rows_max < rows_min || n < rows_min || n > rows_max || row_lo < 0) {
+        if (!ctx) return ALQ_ERR_INVALID;
+        ALQ_FAIL(ctx, ALQ_ERR_INVALID, "alq_uncertainty_tail_sharded: n = %lld outside [rows_min, rows_max] = [%lld, %lld]", (long long)n,
+                 (long long)rows_min, (long long)rows_max);
+    }
+    return uncertainty_tail_impl(ctx, logits, n, c, ld, mode, b, scores, out_gpos, stream, true, row_lo, rows_min, rows_max);
 }
 
 extern "C" int alq_badge_factors(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld,

@@ -127,6 +127,19 @@ class Engine:
                                                   self._stream()), "alq_uncertainty_tail")
         return scores, out
 
+    def uncertainty_tail_sharded(self, logits: torch.Tensor, mode: int, b: int, row_lo: int, rows_min: int, rows_max: int,
+                                 scores_out: Optional[torch.Tensor] = None):
+        """K1 + K1b + the cross-GPU exchange in one call (one cooperative launch per rank when the fused path applies):
+        (scores [n] of this shard, global positions [b] int32 -- identical on every rank).  Collective over comm_init's group."""
+        logits = _f32c(logits, "logits")
+        n, c = logits.shape
+        scores = scores_out if scores_out is not None else torch.empty(max(n, 1), dtype=torch.float32, device=logits.device)
+        out = torch.empty(int(b), dtype=torch.int32, device=logits.device)
+        self._check(self.lib.alq_uncertainty_tail_sharded(self._h, _ptr(logits), n, c, _ld(logits) if n else c, mode, int(b), int(row_lo),
+                                                          int(rows_min), int(rows_max), _ptr(scores), _ptr(out), self._stream()),
+                    "alq_uncertainty_tail_sharded")
+        return scores, out
+
     def topb_pack(self, scores: torch.Tensor, pos: torch.Tensor, row_lo: int, b_pad: int,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Local winners as packed (score key << 32 | global position) int64 words, ~0-padded to b_pad."""

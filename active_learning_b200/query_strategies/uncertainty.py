@@ -55,6 +55,19 @@ class UncertaintyQuery(EngineMixin):
         logits, _ = self._forward_pool(idxs_for_query[lo:hi], self.net, want_features=False)
         self.net.train()
         eng = self.get_engine()
+        if getattr(eng, "comm_ready", False) and hasattr(eng, "uncertainty_tail_sharded"):
+            # K1 + K1b + the exchange as one launch per rank (peer-memory windows); one barrier first: the forward passes
+            # of the ranks can drift apart by seconds and the in-kernel waits are bounded
+            import torch.distributed as dist
+            sizes = [b_ - a_ for a_, b_ in (group.row_range(n, q) for q in range(group.world_size))]
+            dist.barrier(group=group.pg)
+            _, gpos = eng.uncertainty_tail_sharded(logits, self.MODE, budget, lo, min(sizes), max(sizes))
+            host = gpos.cpu().numpy()
+            try:
+                eng.comm_check()
+                return host.astype(np.int64) & 0xFFFFFFFF
+            except Exception:                       # a peer never showed up: the collective path below
+                pass
         b_loc = min(budget, hi - lo)
         scores, pos_loc = self._tail(eng, logits, b_loc)
         return group.merge_smallest(scores, pos_loc, lo, budget, eng, rendezvous=True)

@@ -742,12 +742,22 @@ def run_own(args):
             with torch.cuda.stream(streams[k]):
                 if pair is not None:
                     pair[0].record()
-                _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)   # K1 + K1b: ONE cooperative launch
-                if pair is not None:
-                    pair[1].record()
                 if group is None:
+                    _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)   # K1 + K1b: ONE cooperative launch
+                    if pair is not None:
+                        pair[1].record()
                     host_out[i & 1].copy_(pos, non_blocking=True)
+                elif getattr(e, "comm_ready", False):
+                    # K1 + K1b + the cross-GPU exchange: ONE cooperative launch per rank (histograms summed and candidates
+                    # gathered through the peer-memory windows from inside the kernel)
+                    _, gp = e.uncertainty_tail_sharded(logits, MODE_MARGIN, BUDGET, row_lo, N_ROWS, N_ROWS, scores_out=sc)
+                    if pair is not None:
+                        pair[1].record()
+                    host_out[i & 1].copy_(gp, non_blocking=True)
                 else:
+                    _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)
+                    if pair is not None:
+                        pair[1].record()
                     gp = group.merge_smallest(sc, pos, row_lo, BUDGET, e, to_host=False)   # all-gather + device merge
                     host_out[i & 1].copy_(gp, non_blocking=True)
 
@@ -805,6 +815,16 @@ def run_own(args):
     ms_step = ms_total / args.steps
     value = N_ROWS * world / (ms_step * 1e-3)
     assert len(res) == BUDGET
+    headline_match = None
+    if group is not None:
+        # the exchanged global top-B against ONE GPU selecting from the concatenated scores of all ranks
+        all_scores = torch.empty(N_ROWS * world, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(all_scores, scores)
+        ref_pos = eng.select_smallest(all_scores, BUDGET).cpu()
+        same = torch.tensor([int(torch.equal(ref_pos, res.cpu()))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        headline_match = bool(same.item())
+        del all_scores
 
     # ---- e2e: host buffers through the C-ABI entry point (H2D + K1 + K1b + D2H) ----------------------
     host_logits = torch.empty((N_ROWS, N_CLASSES), dtype=torch.float32).pin_memory()
@@ -836,6 +856,7 @@ def run_own(args):
                 "h2d_bytes_per_step": N_ROWS * N_CLASSES * 4, "d2h_bytes_per_step": BUDGET * 4,
                 "ms_per_step": e2e_s * 1e3, "api": "alq_uncertainty_query_host (pinned host logits)"},
         "gpu_launches": int(launches),
+        "picks_match_single_gpu": headline_match,
         "host_enqueue_ms_per_step": (t_enq - t_w0) * 1e3 / args.steps,
         "latency_ms_single_query": latency_ms,
         "pipelined": pipelined,

@@ -88,6 +88,19 @@ int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
 int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
                          int64_t b, float* scores, int32_t* out_pos, void* stream);
 
+/* The same tail with the rows sharded over the G ranks of the peer-memory group (alq_comm_create/connect): rank r holds
+ * `n` rows that are positions [row_lo, row_lo + n) of the pool and every rank receives the same out_gpos[0..b): the global
+ * positions of the b smallest scores over ALL ranks, ascending (score, position) -- exactly what a single GPU returns for
+ * the concatenated pool.  K1, K1b and the exchange are ONE cooperative launch per rank: both histogram levels are summed over
+ * the ranks and the b + few candidate words gathered through the windows from inside the kernel (8-byte {tag, value} words
+ * and plain stores over NVLink; no collective library, nothing on the host).  Collective: every rank calls it with the same
+ * c, mode, b, rows_min / rows_max (the smallest / largest shard; they decide, identically on every rank, whether the fused
+ * kernel applies -- otherwise K1, K1b and alq_topb_exchange run back to back, same result).  Asynchronous; a peer that never
+ * shows up is reported through alq_comm_check like alq_topb_exchange.                                              */
+int alq_uncertainty_tail_sharded(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
+                                 int64_t b, int64_t row_lo, int64_t rows_min, int64_t rows_max, float* scores,
+                                 int32_t* out_gpos, void* stream);
+
 /* Multi-GPU top-B (rows sharded over G ranks): each rank packs its local winners as
  * out[i] = ord(scores[pos[i]]) << 32 | (row_lo + pos[i])  (i < k; padded with ~0 up to b_pad),
  * the G*b_pad words are all-gathered by the caller (NCCL), and alq_topb_merge returns the global

@@ -90,6 +90,49 @@ if not (len(sys.argv) > 1 and sys.argv[1] == "bigonly"):
 if len(sys.argv) > 1 and sys.argv[1] in ("big", "bigonly"):
     case(80000, 50000, 2048, 0, 2000, False, 5)
     case(80000, 50000, 2048, 1000, 2000, False, 6)
+
+
+def tail_case(n_per, c, b, seed, dyadic=False):
+    """K1 + K1b + exchange as one launch per rank vs one GPU on the concatenated pool (uneven shards too)."""
+    global ok
+    g = torch.Generator(device=dev).manual_seed(seed)
+    sizes = [n_per + (37 * q if seed % 2 else 0) for q in range(world)]
+    n_tot = sum(sizes)
+    if dyadic:
+        logits = torch.randint(-2, 3, (n_tot, c), generator=g, device=dev).float()
+    else:
+        logits = torch.randn(n_tot, c, generator=g, device=dev) * 3
+    lo = sum(sizes[:rank])
+    shard = logits[lo:lo + sizes[rank]].contiguous()
+    for mode in (0, 1, 2):
+        _, ref = eng.uncertainty_tail(logits, mode, b)
+        torch.cuda.synchronize()
+        dist.barrier()
+        _, got = eng.uncertainty_tail_sharded(shard, mode, b, lo, min(sizes), max(sizes))
+        torch.cuda.synchronize()
+        eng.comm_check()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        for _ in range(20):
+            eng.uncertainty_tail_sharded(shard, mode, b, lo, min(sizes), max(sizes))
+        e1.record()
+        torch.cuda.synchronize()
+        same = torch.tensor([int(torch.equal(ref, got))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            rec = {"tail": True, "rows_per_rank": sizes, "c": c, "budget": b, "mode": mode, "dyadic": dyadic, "world": world,
+                   "picks_match_single_gpu": bool(same.item()), "us_per_call": e0.elapsed_time(e1) * 1e3 / 20}
+            report.append(rec)
+            print(json.dumps(rec), flush=True)
+        ok = ok and bool(same.item())
+
+
+tail_case(20000, 1000, 10000, 11)
+tail_case(9000, 64, 3000, 12, dyadic=True)
+tail_case(4200, 1000, 700, 13)
+if len(sys.argv) > 1 and sys.argv[1] in ("big", "bigonly"):
+    tail_case(80000, 1000, 10000, 14)
 dist.barrier()
 if rank == 0:
     print("MGPU GREEDY", "PASS" if ok else "FAIL", flush=True)

@@ -498,58 +498,72 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
     }
     __syncthreads();
     if (dbg) dbg[2] = clock64();
-    // ---- the whole list into shared memory: one bulk copy per rank segment (segments padded to an even word count) ----
+    // ---- the list = the rank segments one after the other (each padded to an even word count with a ~0 word that sorts
+    //      behind everything).  CTA c ranks slice c of it against all of it. ----
     int seg_off[ALQ_MAX_WORLD + 1];
     seg_off[0] = 0;
-    for (int r = 0; r < W; ++r) seg_off[r + 1] = seg_off[r] + static_cast<int>((min(s_tot[r], static_cast<uint32_t>(S.cand_cap)) + 1u) & ~1u);
+    bool overflow = false;
+    for (int r = 0; r < W; ++r) {
+        overflow = overflow || s_tot[r] > static_cast<uint32_t>(S.cand_cap);
+        seg_off[r + 1] = seg_off[r] + static_cast<int>((min(s_tot[r], static_cast<uint32_t>(S.cand_cap)) + 1u) & ~1u);
+    }
     const int M = seg_off[W];
+    const int perc = (M + grid - 1) / grid, s0 = min(M, static_cast<int>(blockIdx.x) * perc), n2 = min(M, s0 + perc) - s0;
+    if (overflow || n2 > S.list_cap) {        // a tie group larger than the windows were sized for: every rank sees the same
+        if (tid == 0) { *reinterpret_cast<volatile int*>(S.status) = ALQ_ERR_STATE; __threadfence_system(); }   // counts and gives up
+        return;
+    }
+    const unsigned long long* cand = reinterpret_cast<const unsigned long long*>(win + S.cand_off);
+    auto list_word = [&](int j) -> unsigned long long {     // word j of the padded list, from this rank's window
+        int r = 0;
+        while (r + 1 < W && j >= seg_off[r + 1]) ++r;
+        const int k = j - seg_off[r];
+        return k < static_cast<int>(s_tot[r]) ? __ldcg(cand + static_cast<size_t>(r) * S.cand_cap + k) : ~0ull;
+    };
+    {
+        unsigned long long* tmp = buf + buf_cap;            // [list_cap] words behind the chunk buffer
+        for (int i = tid; i < n2; i += nthr) tmp[i] = list_word(s0 + i);
+        __syncthreads();
+        for (int i = tid; i < n2; i += nthr) {              // own slice sorted (rank by counting; equal pad words keep
+            const unsigned long long w = tmp[i];            // distinct slots)
+            int r = 0;
+            for (int q = 0; q < n2; ++q) {
+                const unsigned long long x = tmp[q];
+                r += (x < w) || (x == w && q < i);
+            }
+            s_list[r] = w;
+        }
+    }
+    for (int i = tid; i <= n2; i += nthr) s_hist[i] = 0;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_misc + 8);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (M > buf_cap) {                        // does not fit (the host sizes the buffer for b + slack): report, never guess
-        if (tid == 0) { *reinterpret_cast<volatile int*>(S.status) = ALQ_ERR_STATE; __threadfence_system(); }
-        return;
-    }
-    if (tid == 0 && M > 0) {
-        mbar_expect_tx(bar, static_cast<uint32_t>(M) * 8u);
-        for (int r = 0; r < W; ++r)
-            if (seg_off[r + 1] > seg_off[r])
-                bulk_g2s(buf + seg_off[r], win + S.cand_off + static_cast<size_t>(r) * S.cand_cap * 8,
-                         static_cast<uint32_t>(seg_off[r + 1] - seg_off[r]) * 8u, bar);
-    }
-    if (M > 0) mbar_wait(bar, 0);
-    if (tid < W && (s_tot[tid] & 1u)) buf[seg_off[tid] + s_tot[tid]] = ~0ull;       // the pad word sorts behind everything
-    __syncthreads();
+    uint32_t phase = 0;
     if (dbg) dbg[3] = clock64();
-    // ---- CTA c ranks slice c of the list ----
-    const int perc = (M + grid - 1) / grid, s0 = min(M, static_cast<int>(blockIdx.x) * perc), n2 = min(M, s0 + perc) - s0;
-    {
-        unsigned long long* tmp = buf + buf_cap;            // [list_cap] words behind the chunk buffer
-        for (int i = tid; i < n2; i += nthr) {
-            const unsigned long long w = buf[s0 + i];
-            int r = 0;
-            for (int q = 0; q < n2; ++q) {
-                const unsigned long long x = buf[s0 + q];
-                r += (x < w) || (x == w && q < i);          // pads (equal ~0 words) keep distinct slots
+    for (int r = 0; r < W; ++r) {
+        const int tot_r = static_cast<int>(s_tot[r]);
+        for (int base = 0; base < tot_r; base += buf_cap) { // one TMA bulk copy per chunk of a rank segment
+            const int m = min(buf_cap, tot_r - base);
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t bytes = static_cast<uint32_t>((m + 1) & ~1) * 8u;
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(buf, cand + static_cast<size_t>(r) * S.cand_cap + base, bytes, bar);
             }
-            tmp[r] = w;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            for (int j = tid; j < m; j += nthr) {
+                const unsigned long long x = buf[j];
+                int lo = 0, hi = n2;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_list[mid] <= x) lo = mid + 1; else hi = mid;
+                }
+                atomicAdd(&s_hist[lo], 1u);
+            }
         }
-        __syncthreads();
-        for (int i = tid; i < n2; i += nthr) s_list[i] = tmp[i];
-    }
-    for (int i = tid; i <= n2; i += nthr) s_hist[i] = 0;
-    __syncthreads();
-    for (int j = tid; j < M; j += nthr) {
-        const unsigned long long x = buf[j];
-        int lo = 0, hi = n2;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_list[mid] <= x) lo = mid + 1; else hi = mid;
-        }
-        atomicAdd(&s_hist[lo], 1u);
     }
     __syncthreads();
     if (warp == 0) {
@@ -1097,8 +1111,8 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
     if (fused && sharded) {
         const int64_t tiles_min = (rows_min + cfg.rows_per_tile - 1) / cfg.rows_per_tile;
         const size_t need = 2 * (static_cast<size_t>(2) * G.world * 2048 * 8 + static_cast<size_t>(G.world) * ctx->sm_count * 8 +
-                                 static_cast<size_t>(G.world) * (b + 4096) * 8 + 1024);
-        fused = tiles_min >= ctx->sm_count && b + 2 * G.world + 64 <= 14000 && need <= AlqComm::kTailRegionBytes &&
+                                 static_cast<size_t>(G.world) * (b / G.world + 4096) * 8 + 1024);
+        fused = tiles_min >= ctx->sm_count && need <= AlqComm::kTailRegionBytes &&
                 G.bytes > G.topb_region_bytes() + AlqComm::kTailRegionBytes && ctx->xchg_status_dev != nullptr;
     }
     if (!fused) {                                   // separate launches: K1, K1b (and the window exchange of the local winners)
@@ -1150,9 +1164,12 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
         sel.row_base = static_cast<unsigned int>(row_lo);
         for (int r = 0; r < G.world; ++r) sel.peer[r] = G.peer[r];
         sel.stride = ctx->sm_count;
-        sel.cand_cap = static_cast<int>(b + 4096);
         const size_t hist_bytes = static_cast<size_t>(2) * G.world * 2048 * 8, cnt_bytes = (static_cast<size_t>(G.world) * sel.stride * 8 + 127) & ~size_t(127);
         const size_t base = G.tail_region_off() + (G.epoch & 1) * (AlqComm::kTailRegionBytes / 2);
+        // a rank's candidate region: whatever the slot leaves (a rank sends at most its rows; normally about b / world words --
+        // only a huge tie group at the threshold can overflow it, and then every rank reports ALQ_ERR_STATE)
+        const size_t room = (AlqComm::kTailRegionBytes / 2 - hist_bytes - cnt_bytes - 256) / (static_cast<size_t>(G.world) * 8);
+        sel.cand_cap = static_cast<int>(std::min<size_t>(room & ~size_t(1), static_cast<size_t>((rows_max + 1) & ~1LL)));
         sel.hist_off = base;
         sel.cnt_off = base + hist_bytes;
         sel.cand_off = sel.cnt_off + cnt_bytes;

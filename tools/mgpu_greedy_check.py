@@ -110,7 +110,12 @@ def tail_case(n_per, c, b, seed, dyadic=False):
         dist.barrier()
         _, got = eng.uncertainty_tail_sharded(shard, mode, b, lo, min(sizes), max(sizes))
         torch.cuda.synchronize()
-        eng.comm_check()
+        try:
+            eng.comm_check()
+        except Exception as exc:              # e.g. a tie group beyond the window regions: reported, never silent
+            if rank == 0:
+                print(json.dumps({"tail": True, "rows_per_rank": sizes, "c": c, "budget": b, "mode": mode, "fused_path_reported": str(exc)[:120]}), flush=True)
+            continue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         e0.record()

@@ -63,6 +63,7 @@ SIGNATURES = {
     "alq_select_smallest": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int64, c_i32p, C.c_void_p]),
     "alq_uncertainty_tail": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int64, c_f32p,
                                        c_i32p, C.c_void_p]),
+    "alq_uncertainty_tail_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "alq_uncertainty_tail_sharded": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                                C.c_int64, C.c_int64, c_f32p, c_i32p, C.c_void_p]),
     "alq_topb_pack": (C.c_int, [C.c_void_p, c_f32p, c_i32p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

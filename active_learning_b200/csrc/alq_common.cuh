@@ -81,6 +81,7 @@ struct alq_ctx {
     int tile_counter_next = 0;
     unsigned int* sel_ring = nullptr;        // ring of zeroed per-launch scratch of the fused score+select kernel
     int sel_ring_next = 0;
+    unsigned int* sel_last_ctr = nullptr;    // counters / stamps of the last fused launch (alq_uncertainty_tail_timing)
     AlqComm comm;
     int k3_impl = 0;          // 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32
     int select_impl = 0;      // 0 auto, 1 multi-kernel radix select, 2 cluster-resident single launch

@@ -250,6 +250,11 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
         if (h) atomicAdd(S.g_hist + i, h);
     }
     sel_grid_barrier(S.g_ctr, gridDim.x);
+    if (blockIdx.x == 0 && tid == 0) {        // every CTA has finished its rows: the stream ends here
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(S.g_ctr + 4)[1] = t;
+    }
     {
         uint32_t hv[4];
 #pragma unroll
@@ -382,6 +387,11 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
         if (r < static_cast<uint32_t>(S.b)) S.out_pos[r] = static_cast<int32_t>(s_list[i] & 0xffffffffu);
     }
     if (dbg) { dbg[5] = clock64(); dbg[6] = total; dbg[7] = nc; }
+    if (blockIdx.x == 0 && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(S.g_ctr + 4)[2] = t;
+    }
 }
 
 __device__ __forceinline__ void sel_ll_store(void* p, unsigned int tag, unsigned int payload) {
@@ -434,6 +444,11 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
             if (h) atomicAdd(S.g_hist + level * 2048 + i, h);
         }
         sel_grid_barrier(S.g_ctr, static_cast<unsigned int>(2 * level + 1) * grid);
+        if (level == 0 && blockIdx.x == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            reinterpret_cast<unsigned long long*>(S.g_ctr + 4)[1] = t;
+        }
         // this CTA's slice of the rank histogram -> every rank; then the same slice summed over the ranks
         for (int i = tid; i < (b_hi - b_lo) * W; i += nthr) {
             const int bin = b_lo + i / W, p = i % W;
@@ -587,6 +602,11 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
         if (r < static_cast<uint32_t>(S.b) && w != ~0ull) S.out_pos[r] = static_cast<int32_t>(w & 0xffffffffu);
     }
     if (dbg) { dbg[4] = clock64(); dbg[5] = clock64(); dbg[6] = M; dbg[7] = n2; }
+    if (blockIdx.x == 0 && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(S.g_ctr + 4)[2] = t;
+    }
 }
 
 // MODE 0..2: scores; MODE 3: BADGE factors (writes a[row, :] and a_norm2[row]);
@@ -609,6 +629,11 @@ rows_pipe_kernel(const float* __restrict__ logits, int64_t n, int c, RowPipeCfg 
     if (sel.b > 0) {
         for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0;
         if (threadIdx.x < 48) s_misc[threadIdx.x] = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            reinterpret_cast<unsigned long long*>(sel.g_ctr + 4)[0] = t;
+        }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = cfg.rows_per_tile;
@@ -1116,6 +1141,7 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
                 G.bytes > G.topb_region_bytes() + AlqComm::kTailRegionBytes && ctx->xchg_status_dev != nullptr;
     }
     if (!fused) {                                   // separate launches: K1, K1b (and the window exchange of the local winners)
+        ctx->sel_last_ctr = nullptr;
         int rc = alq_score_softmax(ctx, logits, n, c, ld, mode, scores, stream);
         if (rc) return rc;
         if (!sharded) return alq_select_smallest(ctx, scores, n, b, out_pos, stream);
@@ -1151,6 +1177,7 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
     sel.g_hist = slot;
     sel.g_ctr = slot + 4 * 2048;
     sel.g_tot = slot + 2 * 2048;
+    ctx->sel_last_ctr = sel.g_ctr;
     static long long* dbg_buf = nullptr;
     if (getenv("ALQ_SELECT_DEBUG")) {
         if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
@@ -1199,6 +1226,19 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
         fprintf(stderr, "[alq fused tail dbg] cycles: level0 %lld level1 %lld candidates %lld load %lld rank %lld | total candidates %lld, CTA 0 holds %lld\n",
                 h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6], h[7]);
     }
+    return ALQ_OK;
+}
+
+// %globaltimer stamps CTA 0 left in the scratch of the LAST fused launch: out_ms[0] = kernel start -> every CTA of this
+// GPU has finished streaming its rows (first grid barrier), out_ms[1] = kernel start -> end.  The caller must have
+// synchronised the stream of that launch.  ALQ_ERR_STATE if the last tail call did not take the fused path.
+extern "C" int alq_uncertainty_tail_timing(alq_ctx* ctx, float* out_ms_host) {
+    if (!ctx || !out_ms_host) return ALQ_ERR_INVALID;
+    if (!ctx->sel_last_ctr) ALQ_FAIL(ctx, ALQ_ERR_STATE, "alq_uncertainty_tail_timing: no fused launch yet");
+    unsigned long long t[3] = {};
+    ALQ_CUDA(ctx, cudaMemcpy(t, ctx->sel_last_ctr + 4, sizeof(t), cudaMemcpyDeviceToHost));
+    out_ms_host[0] = t[1] > t[0] ? static_cast<float>((t[1] - t[0]) * 1e-6) : 0.f;
+    out_ms_host[1] = t[2] > t[0] ? static_cast<float>((t[2] - t[0]) * 1e-6) : 0.f;
     return ALQ_OK;
 }
 

@@ -127,6 +127,13 @@ class Engine:
                                                   self._stream()), "alq_uncertainty_tail")
         return scores, out
 
+    def uncertainty_tail_timing(self):
+        """(stream_ms, kernel_ms) of the last fused tail launch, from in-kernel %globaltimer stamps (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        ms = (C.c_float * 2)()
+        self._check(self.lib.alq_uncertainty_tail_timing(self._h, C.addressof(ms)), "alq_uncertainty_tail_timing")
+        return float(ms[0]), float(ms[1])
+
     def uncertainty_tail_sharded(self, logits: torch.Tensor, mode: int, b: int, row_lo: int, rows_min: int, rows_max: int,
                                  scores_out: Optional[torch.Tensor] = None):
         """K1 + K1b + the cross-GPU exchange in one call (one cooperative launch per rank when the fused path applies):

@@ -815,6 +815,10 @@ def run_own(args):
     ms_step = ms_total / args.steps
     value = N_ROWS * world / (ms_step * 1e-3)
     assert len(res) == BUDGET
+    try:
+        stream_ms, kern_ms = eng.uncertainty_tail_timing()       # in-kernel stamps of the last fused launch
+    except Exception:
+        stream_ms = kern_ms = None
     headline_match = None
     if group is not None:
         # the exchanged global top-B against ONE GPU selecting from the concatenated scores of all ranks
@@ -865,7 +869,12 @@ def run_own(args):
                                "the CUDA events bracket the WHOLE kernel, selection included", "bound": "hbm",
                      "achieved": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9 / peak,
-                     "traffic": ncu_traffic("score_margin"), "kernel_ms": k1_ms, "peak_source": peak_src,
+                     "traffic": ncu_traffic("fused_tail_margin"), "kernel_ms": k1_ms, "peak_source": peak_src,
+                     "streaming_phase": (None if not stream_ms else {
+                         "us": stream_ms * 1e3, "achieved": N_ROWS * (4 * N_CLASSES + 4) / (stream_ms * 1e-3) / 1e9,
+                         "frac": N_ROWS * (4 * N_CLASSES + 4) / (stream_ms * 1e-3) / 1e9 / peak, "kernel_us_in_kernel_clock": kern_ms * 1e3,
+                         "timing": "%globaltimer stamps of CTA 0 inside the fused kernel: start -> every CTA has finished its rows (first "
+                                   "grid barrier); the rest of the kernel is the selection epilogue (and, at N > 1, the exchange)"}),
                      "bytes_per_row": 4 * N_CLASSES + 4},
     }
     if rank == 0:

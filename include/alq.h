@@ -88,6 +88,11 @@ int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
 int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
                          int64_t b, float* scores, int32_t* out_pos, void* stream);
 
+/* Diagnostics of the LAST fused launch of alq_uncertainty_tail[_sharded] on this context (the caller has synchronised its
+ * stream): out_ms_host[0] = kernel start -> every CTA has finished streaming its rows, [1] = kernel start -> end, both from
+ * %globaltimer stamps of CTA 0.  ALQ_ERR_STATE if that call ran the separate kernels instead.                         */
+int alq_uncertainty_tail_timing(alq_ctx* ctx, float* out_ms_host);
+
 /* The same tail with the rows sharded over the G ranks of the peer-memory group (alq_comm_create/connect): rank r holds
  * `n` rows that are positions [row_lo, row_lo + n) of the pool and every rank receives the same out_gpos[0..b): the global
  * positions of the b smallest scores over ALL ranks, ascending (score, position) -- exactly what a single GPU returns for

@@ -455,12 +455,16 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
             sel_ll_store(S.peer[p] + S.hist_off + (static_cast<size_t>(level * W + S.rank) * 2048 + bin) * 8, S.tag,
                          __ldcg(S.g_hist + level * 2048 + bin));
         }
-        for (int i = tid; i < (b_hi - b_lo); i += nthr) {
-            uint32_t sum = 0;
-            for (int r = 0; r < W; ++r)
-                sum += sel_ll_wait(win + S.hist_off + (static_cast<size_t>(level * W + r) * 2048 + b_lo + i) * 8, S.tag, S);
-            S.g_tot[level * 2048 + b_lo + i] = sum;
+        uint32_t* s_sum = reinterpret_cast<uint32_t*>(s_misc + 16);           // [per <= 32] (find_bin's scratch, free here)
+        if (tid < 32) s_sum[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < (b_hi - b_lo) * W; i += nthr) {                 // one word per thread: the waits overlap
+            const int k = i / W, r = i % W;
+            const uint32_t v = sel_ll_wait(win + S.hist_off + (static_cast<size_t>(level * W + r) * 2048 + b_lo + k) * 8, S.tag, S);
+            if (v) atomicAdd(&s_sum[k], v);
         }
+        __syncthreads();
+        for (int i = tid; i < (b_hi - b_lo); i += nthr) S.g_tot[level * 2048 + b_lo + i] = s_sum[i];
         sel_grid_barrier(S.g_ctr, static_cast<unsigned int>(2 * level + 2) * grid);
         {
             uint32_t hv[4];

@@ -32,6 +32,7 @@ class CoresetQuery(EngineMixin):
         self.subset_labeled = kwargs["subset_labeled"]
         self.subset_unlabeled = kwargs["subset_unlabeled"]
         self.cache_embeddings = kwargs.get("cache_embeddings", True)
+        self.channels_last = kwargs.get("channels_last", True)
 
     # ---- coreset_sampler.py:21-41 ------------------------------------------------------------------
     def get_idxs_for_coreset(self, return_sep_idxs=False):

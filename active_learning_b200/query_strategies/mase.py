@@ -20,6 +20,7 @@ class MASEQuery(EngineMixin):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.cache_embeddings = kwargs.get("cache_embeddings", True)
+        self.channels_last = kwargs.get("channels_last", True)
         self.mase_self_check = kwargs.get("mase_self_check", True)
 
     # ---- mase_sampler.py:19-27 ---------------------------------------------------------------------

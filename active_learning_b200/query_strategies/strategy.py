@@ -155,6 +155,62 @@ class EngineMixin:
         return DataLoader(Subset(self.al_set if dataset is None else dataset, indices=idxs), shuffle=False,
                           **self.train_args["loader_te_args"], drop_last=False)
 
+    # ---- pool-forward data path -----------------------------------------
+    def _device_batches(self, loader, dev, net=None):
+        """The loader's batches with x already on the device: batch k+1 is staged through one of two pinned host buffers
+        and copied on a side stream while batch k runs through the network, so the H2D copy and the host-side collation
+        overlap the forward pass instead of sitting in front of it.  Image batches (4-D) are handed over channels-last and
+        the network is switched to channels-last once (same arithmetic, the tensor-core-friendly cuDNN kernels; opt out
+        with the sampler kwarg channels_last=False).  Precision is untouched: fp32 weights and activations, torch's
+        defaults for TF32."""
+        dev = torch.device(dev)
+        if dev.type != "cuda":
+            for x, y, i in loader:
+                yield x.to(dev), y, i
+            return
+        cl = bool(getattr(self, "channels_last", True))
+        if cl and net is not None and not getattr(net, "_alq_channels_last", False):
+            try:
+                net.to(memory_format=torch.channels_last)
+                net._alq_channels_last = True
+            except Exception:
+                cl = False
+        side = torch.cuda.Stream(device=dev)
+        pinned = [None, None]
+
+        def stage(batch, slot):
+            x, y, i = batch
+            if not x.is_pinned():
+                if pinned[slot] is None or pinned[slot].shape != x.shape or pinned[slot].dtype != x.dtype:
+                    pinned[slot] = torch.empty(x.shape, dtype=x.dtype).pin_memory()
+                pinned[slot].copy_(x)
+                x = pinned[slot]
+            with torch.cuda.stream(side):
+                xd = x.to(dev, non_blocking=True)
+                if cl and xd.dim() == 4:
+                    xd = xd.contiguous(memory_format=torch.channels_last)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return xd, y, i, ev
+
+        it = iter(loader)
+        try:
+            nxt = stage(next(it), 0)
+        except StopIteration:
+            return
+        k = 0
+        while nxt is not None:
+            xd, y, i, ev = nxt
+            k += 1
+            try:
+                nxt = stage(next(it), k & 1)      # the next batch's copy is in flight while this one is consumed
+            except StopIteration:
+                nxt = None
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            xd.record_stream(cur)
+            yield xd, y, i
+
     # ---- cross-round embedding cache (SURVEY.md section 8f, rank 1) ---------------------------------
     def _cacheable(self, net):
         """Under --freeze_feature the encoder never changes (resnet_simclr.py:36-37 detaches it) and the
@@ -167,16 +223,22 @@ class EngineMixin:
     def _encoder_fingerprint(net):
         """Every parameter AND buffer of the encoder (BatchNorm running statistics included): a partially loaded
         checkpoint, changed BN statistics or a fine-tuned last block must invalidate the cached embeddings.  Two
-        moments per tensor in fp64; runs once per query (a few ms for ResNet-50)."""
+        moments per tensor, reduced on the tensor's own device and fetched with ONE transfer (no per-tensor sync:
+        a ResNet-50 has 320 state tensors); runs once per query."""
         with torch.no_grad():
             sd = net.encoder.state_dict()
             if not sd:
                 return (0,)
-            fp = [len(sd)]
+            names, shapes, moments = [], [], []
             for name, t in sd.items():
-                t64 = t.detach().double().flatten()
-                fp.append((name, tuple(t.shape), float(t64.sum()), float((t64 * t64).sum())))
-            return tuple(fp)
+                t = t.detach()
+                tf = t if t.is_floating_point() else t.double()
+                names.append(name)
+                shapes.append(tuple(t.shape))
+                moments.append(tf.sum(dtype=torch.float64))
+                moments.append(torch.linalg.vector_norm(tf.flatten(), 2, dtype=torch.float64))
+            vals = torch.stack(moments).cpu().tolist()
+            return (len(sd), tuple(names), tuple(shapes), tuple(vals))
 
     def _forward_pool_cached(self, idxs, net, want_features):
         """Same outputs as `_forward_pool`, but the encoder runs only for pool rows it has not seen: the
@@ -199,8 +261,8 @@ class EngineMixin:
             missing = np.asarray(idxs, dtype=np.int64) if have is None else np.asarray(idxs, dtype=np.int64)[(~have).cpu().numpy()]
             if len(missing):
                 off = 0
-                for x, _y, _i in self._loader(missing.tolist()):
-                    em = net.encoder(x.to(dev, non_blocking=True))
+                for x, _y, _i in self._device_batches(self._loader(missing.tolist()), dev, net):
+                    em = net.encoder(x)
                     if cache is None:
                         dpad = (em.shape[1] + 3) & ~3
                         cache = {"fp": fp, "dim": em.shape[1],
@@ -233,10 +295,9 @@ class EngineMixin:
         logits = emb = None
         off = 0
         with torch.no_grad():
-            for x, _y, _i in self._loader(idxs, dataset):
+            for x, _y, _i in self._device_batches(self._loader(idxs, dataset), dev, net):
                 if labels_out is not None:
                     labels_out.append(torch.as_tensor(_y).clone())
-                x = x.to(dev, non_blocking=True)
                 if want_features:
                     lg, em = net(x, return_features="finalembed")
                 else:

@@ -22,6 +22,7 @@ class UncertaintyQuery(EngineMixin):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.cache_embeddings = kwargs.get("cache_embeddings", True)
+        self.channels_last = kwargs.get("channels_last", True)
 
     def query(self, budget):
         idxs_for_query = self.available_query_idxs(boolean=False, shuffle=self.SHUFFLE_POOL)

@@ -606,7 +606,7 @@ def run_mase_workload(eng, peak, steps, warmup, rank=0):
     }
 
 
-def run_pool_forward_workload(eng, images=1024, batch=128):
+def run_pool_forward_workload(eng, images=2048, batch=128):
     """the query END TO END through the public sampler API -- DataLoader over host
     images -> H2D -> ResNet-50 in the reference's layout (torchvision encoder + linear head, resnet_simclr.py:6-41,
     random init, torch defaults) -> logits slab -> K1 + K1b -> indices on the host.  Then the same under
@@ -657,25 +657,33 @@ def run_pool_forward_workload(eng, images=1024, batch=128):
     budget = images // 8
     out = {"workload": "MarginSampler.query end to end (synthetic 3x224x224 pool -> ResNet-50 fp32 forward -> K1 + K1b)",
            "images": images, "batch_size": batch, "budget": budget,
-           "precision": "torch defaults: fp32 weights/activations, cuDNN conv TF32 allowed, matmul fp32"}
-    for tag, freeze in (("uncached", False), ("freeze_feature_cached", True)):
-        kw = dict(early_stop_patience=0, n_epoch=1, world_size=1, model="SSLResNet50", freeze_feature=freeze,
-                  ckpt_path=tempfile.mkdtemp(prefix="alq_bench_"), exp_name="b")
-        s = get_strategy("MarginSampler")(ds, ds, net, {"loader_te_args": {"batch_size": batch, "num_workers": 0, "pin_memory": True}},
-                                          np.array([], dtype=np.int64), Exp(), None, **kw)
-        s.init_network_weights()
-        s.set_engine(eng)
-        times = []
-        sync = torch.cuda.synchronize if torch.cuda.is_available() else (lambda: None)
-        for _ in range(3):                       # query 0 warms cuDNN / fills the cache; 1-2 are timed
-            sync()
-            t0 = time.perf_counter()
-            idx, cost = s.query(float(budget))
-            sync()
-            times.append(time.perf_counter() - t0)
-        assert cost == budget and len(set(idx)) == budget
-        dt = min(times[1:])
-        out[tag] = {"value": images / dt, "unit": "samples/s", "ms_per_query": dt * 1e3, "first_query_ms": times[0] * 1e3}
+           "precision": "torch defaults: fp32 weights/activations, cuDNN conv TF32 allowed, matmul fp32",
+           "data_path": "pinned double-buffered H2D on a side stream, channels-last network and batches (EngineMixin._device_batches)"}
+    # loader arguments: the reference's ImageNet arg pool (arg_pools/ssp_linear_evaluation.py:12-16: 8 workers, prefetch 2) and,
+    # for comparison with round 1, a single-process loader
+    loaders = {"": {"batch_size": batch, "num_workers": 8, "prefetch_factor": 2, "pin_memory": True},
+               "_single_process_loader": {"batch_size": batch, "num_workers": 0, "pin_memory": True}}
+    for suffix, largs in loaders.items():
+        for tag, freeze in (("uncached", False), ("freeze_feature_cached", True)):
+            if suffix and freeze:
+                continue
+            kw = dict(early_stop_patience=0, n_epoch=1, world_size=1, model="SSLResNet50", freeze_feature=freeze,
+                      ckpt_path=tempfile.mkdtemp(prefix="alq_bench_"), exp_name="b")
+            s = get_strategy("MarginSampler")(ds, ds, net, {"loader_te_args": dict(largs)}, np.array([], dtype=np.int64), Exp(), None, **kw)
+            s.init_network_weights()
+            s.set_engine(eng)
+            times = []
+            sync = torch.cuda.synchronize if torch.cuda.is_available() else (lambda: None)
+            for _ in range(3):                       # query 0 warms cuDNN / fills the cache; 1-2 are timed
+                sync()
+                t0 = time.perf_counter()
+                idx, cost = s.query(float(budget))
+                sync()
+                times.append(time.perf_counter() - t0)
+            assert cost == budget and len(set(idx)) == budget
+            dt = min(times[1:])
+            out[tag + suffix] = {"value": images / dt, "unit": "samples/s", "ms_per_query": dt * 1e3, "first_query_ms": times[0] * 1e3,
+                                 "loader": largs}
     net.cpu()
     return out
 

@@ -164,11 +164,11 @@ class EngineMixin:
         with the sampler kwarg channels_last=False).  Precision is untouched: fp32 weights and activations, torch's
         defaults for TF32."""
         dev = torch.device(dev)
-        if dev.type != "cuda":
+        if dev.type != "cuda" or os.environ.get("ALQ_PREFETCH", "1") == "0":
             for x, y, i in loader:
-                yield x.to(dev), y, i
+                yield x.to(dev, non_blocking=True), y, i
             return
-        cl = bool(getattr(self, "channels_last", True))
+        cl = bool(getattr(self, "channels_last", True)) and os.environ.get("ALQ_CHANNELS_LAST", "1") != "0"
         if cl and net is not None and not getattr(net, "_alq_channels_last", False):
             try:
                 net.to(memory_format=torch.channels_last)

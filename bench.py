@@ -661,8 +661,8 @@ def run_pool_forward_workload(eng, images=2048, batch=128):
            "data_path": "pinned double-buffered H2D on a side stream, channels-last network and batches (EngineMixin._device_batches)"}
     # loader arguments: the reference's ImageNet arg pool (arg_pools/ssp_linear_evaluation.py:12-16: 8 workers, prefetch 2) and,
     # for comparison with round 1, a single-process loader
-    loaders = {"": {"batch_size": batch, "num_workers": 8, "prefetch_factor": 2, "pin_memory": True},
-               "_single_process_loader": {"batch_size": batch, "num_workers": 0, "pin_memory": True}}
+    loaders = {"": {"batch_size": batch, "num_workers": 8, "prefetch_factor": 2},
+               "_single_process_loader": {"batch_size": batch, "num_workers": 0}}
     for suffix, largs in loaders.items():
         for tag, freeze in (("uncached", False), ("freeze_feature_cached", True)):
             if suffix and freeze:

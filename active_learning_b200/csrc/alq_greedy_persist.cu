@@ -575,15 +575,12 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
     const int cw = warp - 1;
     const int C = cfg.consumers;              // warps that take tiles (<= kConsWarps)
     char* const win = A.peer[A.rank];
-    const int K = G.n_leaves;
-    const int root = K > 1 ? 2 * K - 2 : 0;
     const float4* q4 = reinterpret_cast<const float4*>(sq);
     unsigned long long* const valw = A.valw + (SAMPLE ? G.cfull_off : 0);
 
     // D^2 sampling: the leaf this 8-lane group owns for the whole call (one per group), the rows behind its
     // positions (shared memory) and which of this lane's 16 positions hold a candidate at all
     const int grp = ct >> 3, g_lane = ct & 7;
-    const unsigned gmask = 0xffu << ((lane >> 3) * 8);
     int my_leaf = -1, leaf_pos = 0, leaf_len = 0;
     unsigned int cand_mask = 0;
     if (SAMPLE) {

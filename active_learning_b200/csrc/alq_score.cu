@@ -239,7 +239,7 @@ __device__ __forceinline__ void sel_find_bin(const uint32_t* hist, uint32_t k, u
 // candidates, [5] level-1 bin
 __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist, unsigned long long* s_list, int* s_misc,
                                              unsigned long long* buf, int buf_cap) {
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     long long* dbg = (S.dbg && blockIdx.x == 0 && tid == 0) ? S.dbg : nullptr;
     __syncthreads();                                        // every consumer warp has appended its rows
     if (dbg) dbg[0] = clock64();

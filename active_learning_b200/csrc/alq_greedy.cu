@@ -12,7 +12,10 @@
 // gradient embedding is never formed:  <g_i,g_q> = <a_i,a_q><h_i,h_q>,  |g|^2 = |a|^2|h|^2.
 // Partitions are a batch dimension: every launch advances all partitions by one step.
 //
-// The streaming kernel is HBM-bound: 4*d (+4*c) + 12 bytes per row per step.  Two variants:
+// This file holds the entry point and the ONE-LAUNCH-PER-STEP variants (single GPU; kept as fallback and as the
+// comparison the persistent kernel is tested against).  The default, and the only multi-GPU form, is variant 3 in
+// alq_greedy_persist.cu: one persistent cooperative launch for the whole loop.
+// The streaming kernel is HBM-bound: 4*d (+4*c) + 12 bytes per row per step.  Two variants here:
 //   variant 1  direct 128-bit L1-bypassing loads, one warp per row;
 //   variant 2  warp-specialised: one producer lane feeds a ring of shared-memory stages with
 //              cp.async.bulk (TMA bulk copies, mbarrier complete_tx), consumer warps do the dots.

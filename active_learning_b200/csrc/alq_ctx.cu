@@ -69,6 +69,7 @@ extern "C" int alq_set_option(alq_ctx* ctx, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "k3_impl" && value >= 0 && value <= 2) ctx->k3_impl = static_cast<int>(value);
     else if (k == "greedy_variant" && value >= 0 && value <= 3) ctx->greedy_variant = static_cast<int>(value);
+    else if (k == "l2_resident_mb" && value >= 0 && value <= 4096) ctx->l2_resident_mb = static_cast<int>(value);
     else if (k == "d2_fast_path" && value >= 0 && value <= 1) ctx->d2_fast_path = static_cast<int>(value);
     else if (k == "spin_timeout_ms" && value >= 1 && value <= 3600000) ctx->spin_timeout_ms = static_cast<int>(value);
     else if (k == "select_impl" && value >= 0 && value <= 2) ctx->select_impl = static_cast<int>(value);

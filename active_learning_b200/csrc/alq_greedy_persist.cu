@@ -72,6 +72,8 @@ struct PersistArgs {
     unsigned int ready_off;        // u64 ready[world] at the head of every window
     unsigned long long ready_tag;
     unsigned int tag_base;         // 0x80000000 | (epoch & 0x7f) << 24
+    int resident_rows;             // rows at the head of every CTA's segment fetched L2::evict_last (they stay in L2 across
+                                   // steps; the rest is fetched evict_first).  0: no hints
     int fast_path;                 // D^2 draw: certified per-CTA-mass path first (0: always the exact NumPy-tree machinery)
     long long timeout_cycles;
 };
@@ -535,6 +537,8 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
         // ===== producer: one lane issues every bulk copy of every step; it never needs the centre =====
         if (lane == 0 && ntiles > 0) {
             const bool contig_x = (A.ldx == d), contig_a = FACTORED && (A.lda == c);
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+            const bool hints = A.resident_rows > 0;
             int s = 0;
             unsigned int par = 0;                     // parity of the `empty` phase to wait for (first round: none)
             bool first_round = true;
@@ -545,16 +549,19 @@ greedy_persist_kernel(const __grid_constant__ PersistArgs A, const PipeCfg cfg, 
                     const int rr = min(R, seg.row_hi - row0);
                     float* tx = tiles + static_cast<size_t>(s) * cfg.tile_floats;
                     float* ta = tx + static_cast<size_t>(R) * d;
+                    const uint64_t pol = (i * R < A.resident_rows) ? pol_keep : pol_stream;
                     mbar_expect_tx(&full[s], static_cast<uint32_t>(rr) * static_cast<uint32_t>(d + c) * 4u);
                     if (contig_x) {
-                        bulk_g2s(tx, A.x + static_cast<long long>(row0) * A.ldx, static_cast<uint32_t>(rr) * d * 4u, &full[s]);
+                        if (hints) bulk_g2s_hint(tx, A.x + static_cast<long long>(row0) * A.ldx, static_cast<uint32_t>(rr) * d * 4u, &full[s], pol);
+                        else bulk_g2s(tx, A.x + static_cast<long long>(row0) * A.ldx, static_cast<uint32_t>(rr) * d * 4u, &full[s]);
                     } else {
                         for (int r = 0; r < rr; ++r)
                             bulk_g2s(tx + static_cast<size_t>(r) * d, A.x + static_cast<long long>(row0 + r) * A.ldx, d * 4u, &full[s]);
                     }
                     if (FACTORED) {
                         if (contig_a) {
-                            bulk_g2s(ta, A.a + static_cast<long long>(row0) * A.lda, static_cast<uint32_t>(rr) * c * 4u, &full[s]);
+                            if (hints) bulk_g2s_hint(ta, A.a + static_cast<long long>(row0) * A.lda, static_cast<uint32_t>(rr) * c * 4u, &full[s], pol);
+                            else bulk_g2s(ta, A.a + static_cast<long long>(row0) * A.lda, static_cast<uint32_t>(rr) * c * 4u, &full[s]);
                         } else {
                             for (int r = 0; r < rr; ++r)
                                 bulk_g2s(ta + static_cast<size_t>(r) * c, A.a + static_cast<long long>(row0 + r) * A.lda, c * 4u, &full[s]);
@@ -1212,6 +1219,11 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
     A.tag_base = static_cast<unsigned int>(ctx->comm.epoch & 0x7fu) << 24 | 0x80000000u;   // never 0: a zeroed word is invalid
     const int clock_khz = ctx->clock_khz;
     A.timeout_cycles = static_cast<long long>(ctx->spin_timeout_ms) * clock_khz;
+    {   // L2 residency: keep `l2_resident_mb` of the rows this GPU streams in L2 across the steps (evict_last), split evenly over the CTAs
+        long long mb = ctx->l2_resident_mb;
+        if (const char* e = getenv("ALQ_L2_RESIDENT_MB")) mb = atoll(e);
+        A.resident_rows = mb > 0 ? static_cast<int>(std::min<long long>((mb << 20) / static_cast<long long>(row_bytes) / std::max(grid, 1), 1 << 30)) : 0;
+    }
     A.fast_path = ctx->d2_fast_path;
     if (const char* e = getenv("ALQ_D2_FAST_PATH")) A.fast_path = atoi(e) != 0;
 

@@ -86,7 +86,8 @@ struct alq_ctx {
     int k3_impl = 0;          // 0 auto, 1 fp32 SIMT, 2 tcgen05 3xTF32
     int select_impl = 0;      // 0 auto, 1 multi-kernel radix select, 2 cluster-resident single launch
     int greedy_variant = 0;   // 0 auto, 1 direct loads, 2 bulk-copy pipeline, 3 persistent cooperative loop
-    int l2_resident_mb = 0;   // persistent selection loop: MB of streamed rows kept in L2 across steps (evict_last hints); 0 = off
+    int l2_resident_mb = 64;  // persistent selection loop: MB of streamed rows kept in L2 across steps (evict_last hints); 0 = off.
+                              // Sweep on one B200 (tools/gpu_r2m.sh): 48-72 MB best, 96 MB worse, 112 MB back to no gain
     int d2_fast_path = 1;     // D^2 draw of the persistent loop: certified per-CTA-mass path first (0: exact tree machinery only)
     int spin_timeout_ms = 20000;   // bounded spins on peer flags (a dead peer must not hang the GPU)
     int base_impl = 0;        // 0 auto, 1 sequential class loop, 2 parallel candidate lists + in-order resolve

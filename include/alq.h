@@ -47,6 +47,9 @@ const char* alq_last_error(const alq_ctx* ctx);
 /* Implementation knobs (defaults pick the fastest valid kernel):
  *   "k3_impl"        0 auto | 1 exact-fp32 SIMT contraction | 2 tcgen05 3xTF32 contraction
  *   "greedy_variant" 0 auto | 1 direct-load step kernel     | 2 bulk-copy (TMA) pipeline | 3 persistent cooperative loop
+ *   "l2_resident_mb" persistent selection loop: MB of the rows a GPU streams that are fetched L2::evict_last (the head of every
+ *                    CTA's segment) so that they stay in the 126 MB L2 across the B steps; the rest is fetched evict_first.
+ *                    Default 64; 0 turns the hints off
  *   "d2_fast_path"   1 (default): the persistent loop's D^2 draw first tries the certified path (one fp64 mass per CTA, the
  *                    rounding of NumPy's float32 probabilities bounded by a margin); 0: always the exact NumPy-tree machinery
  *   "spin_timeout_ms" how long a kernel waits for a peer GPU's flag before giving up with ALQ_ERR_STATE (default 20000)

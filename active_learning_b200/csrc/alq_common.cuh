@@ -122,6 +122,11 @@ struct alq_ctx {
     } while (0)
 
 // Device scratch: returns a 256-byte aligned pointer into the arena, growing it if needed.
+// Grid-synchronising kernels launched WITHOUT the cooperative API (see alq_score.cu) must never share the device with
+// another one of this process: every such launch is bracketed by these two (one event per device, process-wide).
+void alq_gridsync_begin(alq_ctx* ctx, cudaStream_t st);
+void alq_gridsync_end(alq_ctx* ctx, cudaStream_t st);
+
 int alq_scratch_reserve(alq_ctx* ctx, size_t bytes);
 int alq_pinned_reserve(alq_ctx* ctx, size_t bytes);
 int alq_arena2_reserve(alq_ctx* ctx, size_t bytes);

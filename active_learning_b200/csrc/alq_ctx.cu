@@ -1,5 +1,6 @@
 // Context, scratch arenas and error reporting of libalq.
 #include <initializer_list>
+#include <mutex>
 #include <new>
 
 #include "alq_common.cuh"
@@ -58,6 +59,25 @@ extern "C" void alq_destroy(alq_ctx* ctx) {
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     delete ctx;
+}
+
+namespace {
+std::mutex g_gridsync_mu;
+cudaEvent_t g_gridsync_ev[64] = {};
+bool g_gridsync_rec[64] = {};
+}  // namespace
+
+void alq_gridsync_begin(alq_ctx* ctx, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_gridsync_mu);
+    const int d = ctx->device & 63;
+    if (!g_gridsync_ev[d]) cudaEventCreateWithFlags(&g_gridsync_ev[d], cudaEventDisableTiming);
+    if (g_gridsync_ev[d] && g_gridsync_rec[d]) cudaStreamWaitEvent(st, g_gridsync_ev[d], 0);
+}
+
+void alq_gridsync_end(alq_ctx* ctx, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_gridsync_mu);
+    const int d = ctx->device & 63;
+    if (g_gridsync_ev[d]) { cudaEventRecord(g_gridsync_ev[d], st); g_gridsync_rec[d] = true; }
 }
 
 extern "C" const char* alq_last_error(const alq_ctx* ctx) {

@@ -1231,9 +1231,11 @@ int alq_greedy_persist(alq_ctx* ctx, const alq_greedy_desc* D, void* stream) {
         persist_ready_kernel<<<1, 32, 0, st>>>(A);       // after the clears above, in stream order
         ALQ_LAUNCH_CHECK(ctx);
     }
+    alq_gridsync_begin(ctx, st);
     cudaError_t le;
     if (factored) le = sample ? launch_persist<true, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max) : launch_persist<true, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max);
     else le = sample ? launch_persist<false, true>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max) : launch_persist<false, false>(grid, smem, st, A, cfg, k_max, lc_max, ne_max, rm_max);
+    alq_gridsync_end(ctx, st);
     if (le != cudaSuccess) {
         cudaGetLastError();
         ALQ_FAIL(ctx, ALQ_ERR_CUDA, "alq_greedy_select: cooperative launch failed: %s (grid %d, %zu B shared)", cudaGetErrorString(le), grid, smem);

@@ -1013,13 +1013,21 @@ cudaError_t launch_rows_pipe(alq_ctx* ctx, cudaStream_t st, const RowPipeCfg& cf
     const int grid = static_cast<int>(std::min<int64_t>(ctx->sm_count, tiles_total));
     unsigned int* counter = next_tile_counter(ctx, st);
     if (!counter) return cudaErrorMemoryAllocation;
-    if (sel.b > 0) {     // the fused selection synchronises the grid: co-residency must be guaranteed
-        RowPipeCfg cfg_v = cfg;
-        MaseArgs mase_v = mase;
-        SelArgs sel_v = sel;
-        void* args[] = {&logits, &n, &c, &cfg_v, &scores, &bs, &row0, &n_total, &a, &lda, &counter, &mase_v, &sel_v};
-        return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rows_pipe_kernel<NV, MODE>), dim3(grid), dim3(32 * (1 + cfg.consumers)),
-                                           args, smem, st);
+    if (sel.b > 0) {
+        // The fused selection synchronises the grid (and, sharded, the GPUs), so all of its CTAs must become resident: one CTA
+        // per SM by construction (grid <= SM count, > 113 KB of shared memory each).  A cooperative launch would guarantee that,
+        // but cooperative launches are not pipelined by the driver -- every step then waits for a host round trip, and with
+        // one process per GPU a descheduled host thread stalls all ranks for milliseconds (measured at 8 GPUs: steps of
+        // 1-5 ms instead of 0.1).  Ordinary launches are safe as long as no two grid-synchronising kernels of this process
+        // share the device at the same time: they are chained through one event per device (other kernels merely delay the
+        // moment the last CTA becomes resident; they never wait for ours).
+        if (grid > ctx->sm_count) return cudaErrorInvalidConfiguration;
+        alq_gridsync_begin(ctx, st);
+        rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, row0, n_total, a, lda,
+                                                                              counter, mase, sel);
+        const cudaError_t le = cudaGetLastError();
+        alq_gridsync_end(ctx, st);
+        return le;
     }
     rows_pipe_kernel<NV, MODE><<<grid, 32 * (1 + cfg.consumers), smem, st>>>(logits, n, c, cfg, scores, bs, row0, n_total, a, lda,
                                                                           counter, mase, sel);

@@ -398,16 +398,25 @@ __device__ __forceinline__ void sel_ll_store(void* p, unsigned int tag, unsigned
     const unsigned long long v = (static_cast<unsigned long long>(tag) << 32) | payload;
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Bounded spin.  The sticky failure flag that lets every other wait of this launch return at once lives in DEVICE
+// memory (g_ctr[12]); the host-visible status word is mapped host memory and is only WRITTEN, once, on a timeout --
+// polling it from thousands of spinning threads is a PCIe read storm that delays the very launches being waited for
+// (measured at 8 GPUs: once one rank was 30 us late every step took 1-6 ms).
 __device__ __forceinline__ unsigned int sel_ll_wait(const void* p, unsigned int tag, const SelArgs& S) {
     unsigned long long v;
     const long long t0 = clock64();
     for (int spin = 0;; ++spin) {
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
         if (static_cast<unsigned int>(v >> 32) == tag) break;
-        if ((spin & 63) == 63 && (*reinterpret_cast<volatile int*>(S.status) != 0 || clock64() - t0 > S.timeout_cycles)) {
-            *reinterpret_cast<volatile int*>(S.status) = ALQ_ERR_STATE;
-            __threadfence_system();
-            break;
+        if ((spin & 255) == 255) {
+            if (*reinterpret_cast<volatile unsigned int*>(S.g_ctr + 12) != 0) break;
+            if (clock64() - t0 > S.timeout_cycles) {
+                if (atomicExch(S.g_ctr + 12, 1u) == 0u) {
+                    *reinterpret_cast<volatile int*>(S.status) = ALQ_ERR_STATE;
+                    __threadfence_system();
+                }
+                break;
+            }
         }
     }
     return static_cast<unsigned int>(v);

@@ -1,0 +1,5 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_scores.py tests/test_gpu_greedy.py -x -q -m gpu 2>&1 | tail -3
+timeout 300 python bench.py --no-extras 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline']['streaming_phase'], d['step_kernel_ms'], d['pipelined'], d['host_enqueue_ms_per_step'])"

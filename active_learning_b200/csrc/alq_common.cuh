@@ -89,6 +89,8 @@ struct alq_ctx {
     int l2_resident_mb = 64;  // persistent selection loop: MB of streamed rows kept in L2 across steps (evict_last hints); 0 = off.
                               // Sweep on one B200 (tools/gpu_r2m.sh): 48-72 MB best, 96 MB worse, 112 MB back to no gain
     int d2_fast_path = 1;     // D^2 draw of the persistent loop: certified per-CTA-mass path first (0: exact tree machinery only)
+    int tail_buckets = 1;     // fused uncertainty tail on one GPU: route candidates to per-CTA score buckets (0: every CTA ranks
+                              // its candidates against the whole list -- the general route, also the fallback for tie groups)
     int spin_timeout_ms = 20000;   // bounded spins on peer flags (a dead peer must not hang the GPU)
     int base_impl = 0;        // 0 auto, 1 sequential class loop, 2 parallel candidate lists + in-order resolve
     std::string err;

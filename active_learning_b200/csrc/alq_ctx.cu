@@ -62,22 +62,30 @@ extern "C" void alq_destroy(alq_ctx* ctx) {
 }
 
 namespace {
+// Kernels with device-wide spin barriers (the fused tail, the persistent selection loop) need all of their CTAs resident,
+// so two of them must never share the device.  Launches on ONE stream are ordered anyway; only when the stream changes
+// is the previous stream fenced with an event (recorded then, lazily: it also covers whatever was enqueued behind the
+// last such kernel, which only over-synchronises).  begin() .. end() hold the lock across the launch.
 std::mutex g_gridsync_mu;
 cudaEvent_t g_gridsync_ev[64] = {};
-bool g_gridsync_rec[64] = {};
+cudaStream_t g_gridsync_last[64] = {};
+bool g_gridsync_has[64] = {};
 }  // namespace
 
 void alq_gridsync_begin(alq_ctx* ctx, cudaStream_t st) {
-    std::lock_guard<std::mutex> lk(g_gridsync_mu);
+    g_gridsync_mu.lock();
     const int d = ctx->device & 63;
+    if (!g_gridsync_has[d] || g_gridsync_last[d] == st) return;
     if (!g_gridsync_ev[d]) cudaEventCreateWithFlags(&g_gridsync_ev[d], cudaEventDisableTiming);
-    if (g_gridsync_ev[d] && g_gridsync_rec[d]) cudaStreamWaitEvent(st, g_gridsync_ev[d], 0);
+    if (g_gridsync_ev[d] && cudaEventRecord(g_gridsync_ev[d], g_gridsync_last[d]) == cudaSuccess) cudaStreamWaitEvent(st, g_gridsync_ev[d], 0);
+    else cudaGetLastError();            // the previous stream no longer exists: its work is already draining
 }
 
 void alq_gridsync_end(alq_ctx* ctx, cudaStream_t st) {
-    std::lock_guard<std::mutex> lk(g_gridsync_mu);
     const int d = ctx->device & 63;
-    if (g_gridsync_ev[d]) { cudaEventRecord(g_gridsync_ev[d], st); g_gridsync_rec[d] = true; }
+    g_gridsync_last[d] = st;
+    g_gridsync_has[d] = true;
+    g_gridsync_mu.unlock();
 }
 
 extern "C" const char* alq_last_error(const alq_ctx* ctx) {
@@ -91,6 +99,7 @@ extern "C" int alq_set_option(alq_ctx* ctx, const char* key, int64_t value) {
     else if (k == "greedy_variant" && value >= 0 && value <= 3) ctx->greedy_variant = static_cast<int>(value);
     else if (k == "l2_resident_mb" && value >= 0 && value <= 4096) ctx->l2_resident_mb = static_cast<int>(value);
     else if (k == "d2_fast_path" && value >= 0 && value <= 1) ctx->d2_fast_path = static_cast<int>(value);
+    else if (k == "tail_buckets" && value >= 0 && value <= 1) ctx->tail_buckets = static_cast<int>(value);
     else if (k == "spin_timeout_ms" && value >= 1 && value <= 3600000) ctx->spin_timeout_ms = static_cast<int>(value);
     else if (k == "select_impl" && value >= 0 && value <= 2) ctx->select_impl = static_cast<int>(value);
     else if (k == "base_impl" && value >= 0 && value <= 2) ctx->base_impl = static_cast<int>(value);

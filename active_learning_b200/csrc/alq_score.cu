@@ -181,7 +181,19 @@ struct SelArgs {
     long long timeout_cycles;
     int* status;                    // mapped host word (sticky)
     unsigned int* g_tot;            // [2 * 2048] histograms summed over the ranks (local)
+    // bucket route of the ranking stage (one GPU; nullptr: off): candidates are routed to CTA `bucket` by a monotone
+    // function of their score, so a CTA only sorts its own bucket -- see select_epilogue
+    unsigned long long* g_bucket;   // [grid][kBucketLanes][bucket_cap]
+    unsigned int* g_bcnt;           // [grid][kBucketLanes] zeroed
+    int bucket_cap;                 // words per sub-list
+    int no_tree;                    // debug (ALQ_TAIL_NOTREE): binary search over the sorted array instead of the tree
 };
+constexpr int kBucketLanes = 16;
+
+// inverse of alq_ord
+__device__ __forceinline__ float sel_key_to_float(uint32_t key) {
+    return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
 
 __device__ __forceinline__ void sel_grid_barrier(unsigned int* ctr, unsigned int target) {
     __syncthreads();
@@ -235,6 +247,58 @@ __device__ __forceinline__ void sel_find_bin(const uint32_t* hist, uint32_t k, u
     __syncthreads();
 }
 
+// Ranking stage, shared by the one-GPU and the sharded epilogue.  The CTA's own (ascending) candidates are searched
+// once per word of the global list -- about b searches per CTA -- and a plain binary search over a sorted array in
+// shared memory is bound by bank conflicts, not by latency: the probes of step k sit a power-of-two stride apart and
+// fall into one or two banks (measured: 11 k cycles of the 14 k-cycle stage for 10 001 words against 80 candidates).
+// So the candidates are also kept as an implicit perfect search tree in breadth-first order (1-based: children of
+// node k are 2k and 2k + 1; missing nodes hold ~0, which no list word reaches): the probes of one step are contiguous
+// words.  Height h = smallest with 2^h - 1 >= nc; the sorted index r sits at node
+//     k(r) = 2^(h-1-z) + ((r + 1) >> (z + 1)),  z = trailing zeros of r + 1,
+// and after h steps of  k = 2k + (tree[k] <= x)  the count of candidates <= x is k - 2^h.
+__device__ __forceinline__ int sel_tree_height(int nc) { return nc > 0 ? 32 - __clz(nc) : 0; }
+__device__ __forceinline__ int sel_tree_node(int r, int h) {
+    const int t = r + 1, z = __ffs(t) - 1;
+    return (1 << (h - 1 - z)) + (t >> (z + 1));
+}
+// s_diff[number of own candidates <= x] += 1 for every word x of buf[0, m)
+__device__ __forceinline__ void sel_count_into_diff(const unsigned long long* buf, int m, const unsigned long long* tree, int h,
+                                                    uint32_t* s_diff) {
+    constexpr int U = 4;                                    // independent searches in flight per thread: each is a chain
+    const int tid = threadIdx.x, nthr = blockDim.x;         // of h dependent shared-memory loads
+    for (int j0 = tid; j0 < m; j0 += U * nthr) {
+        unsigned long long x[U];
+        int k[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + u * nthr;
+            x[u] = buf[j < m ? j : j0];
+            k[u] = 1;
+        }
+        for (int s = 0; s < h; ++s) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) k[u] = 2 * k[u] + (tree[k[u]] <= x[u] ? 1 : 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j0 + u * nthr < m) atomicAdd(&s_diff[k[u] - (1 << h)], 1u);
+    }
+}
+// the same over the sorted array itself (only when the tree does not fit: nc == list_cap)
+__device__ __forceinline__ void sel_count_into_diff_sorted(const unsigned long long* buf, int m, const unsigned long long* own,
+                                                           int nc, uint32_t* s_diff) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int j = tid; j < m; j += nthr) {
+        const unsigned long long x = buf[j];
+        int lo = 0, hi = nc;                                // first own candidate > x
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (own[mid] <= x) lo = mid + 1; else hi = mid;
+        }
+        atomicAdd(&s_diff[lo], 1u);
+    }
+}
+
 // s_misc: [0] words in s_list, [1] level-0 bin, [2] rank still wanted inside it, [3] offset in g_cand, [4] own
 // candidates, [5] level-1 bin
 __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist, unsigned long long* s_list, int* s_misc,
@@ -261,7 +325,10 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
         for (int k = 0; k < 4; ++k) hv[k] = (tid + k * nthr) < 2048 ? __ldcg(S.g_hist + tid + k * nthr) : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if ((tid + k * nthr) < 2048) s_hist[tid + k * nthr] = hv[k];
+            if ((tid + k * nthr) < 2048) {
+                s_hist[tid + k * nthr] = hv[k];
+                if (hv[k]) atomicMax(&s_misc[6], 2047 - (tid + k * nthr));      // first populated bin (s_misc[6] starts at 0)
+            }
     }
     __syncthreads();
     sel_find_bin(s_hist, static_cast<uint32_t>(S.b), reinterpret_cast<uint32_t*>(s_misc + 16), &s_misc[1], &s_misc[2]);
@@ -299,6 +366,95 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
     __syncthreads();
     const uint32_t T = (T0 << 11) | static_cast<uint32_t>(s_misc[5]);        // 22-bit prefix of the b-th smallest key
     if (dbg) dbg[2] = clock64();
+    unsigned int barriers = 2;
+    // ---- bucket route.  Every candidate score lies in [lo, hi] = [lower edge of the first populated level-0 bin,
+    //      upper edge of prefix T]; bucket(score) = floor((score - lo) * grid / (hi - lo)), clamped, is monotone in the
+    //      key, so bucket q holds exactly the ranks [sum of the counts of buckets < q, ...): each candidate goes to the
+    //      CTA of its bucket, a CTA sorts ITS bucket (about b / grid words) and nobody ranks against the whole list
+    //      (that stage was bound by ~1 shared-memory atomic per list word per CTA: 5.5 us).  Scores that do not spread
+    //      (tie groups, one bucket beyond bucket_cap) or non-finite edges fall through to the general route below;
+    //      every CTA takes the same decision from the same counts. ----
+    if (S.g_bucket) {
+        const int G = static_cast<int>(gridDim.x);
+        const float lo = sel_key_to_float(static_cast<uint32_t>(2047 - s_misc[6]) << 21);
+        const float hi = sel_key_to_float((T << 10) | 0x3ffu);
+        const float scale = static_cast<float>(G) / (hi - lo);
+        const bool spread = isfinite(lo) && isfinite(hi) && hi > lo && isfinite(scale);      // same value in every thread of every CTA
+        if (spread) {
+            // kBucketLanes counters (and sub-lists) per bucket, CTA c appends to lane c % kBucketLanes: ~b appends onto `grid`
+            // addresses is a chain of ~b / grid same-address atomics deep (measured 4 us); sixteen lanes cut it to a few
+            constexpr int R = kBucketLanes;
+            const int lane_id = static_cast<int>(blockIdx.x) % R, sub_cap = S.bucket_cap;
+            if (tid < 3 + R) s_misc[48 + tid] = 0;          // [48] largest sub-list, [49] words in the buckets below mine, [51..] my sub-lists
+            for (int i = tid; i < cnt; i += nthr) {
+                const unsigned long long w = s_list[i];
+                if (static_cast<uint32_t>(w >> 42) <= T) {
+                    const float sc = sel_key_to_float(static_cast<uint32_t>(w >> 32));
+                    const int q = min(G - 1, max(0, __float2int_rd((sc - lo) * scale)));
+                    const unsigned int slot = atomicAdd(S.g_bcnt + q * R + lane_id, 1u);
+                    if (slot < static_cast<unsigned int>(sub_cap))
+                        S.g_bucket[(static_cast<size_t>(q) * R + lane_id) * sub_cap + slot] = w;
+                }
+            }
+            sel_grid_barrier(S.g_ctr, ++barriers * gridDim.x);
+            if (dbg) dbg[3] = clock64();
+            // my bucket's sub-lists are fetched together with the counters (one L2 round trip); what lies beyond a
+            // sub-list's count is dropped once the counts are known
+            const unsigned long long* src = S.g_bucket + static_cast<size_t>(blockIdx.x) * R * sub_cap;
+            unsigned long long wv[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) wv[k] = (tid + k * nthr) < R * sub_cap ? __ldcg(src + tid + k * nthr) : 0ull;
+            {
+                int mx = 0, below = 0;
+                for (int idx = tid; idx < G * R; idx += nthr) {
+                    const int v = static_cast<int>(__ldcg(S.g_bcnt + idx)), q = idx / R;
+                    mx = max(mx, v);
+                    if (q < static_cast<int>(blockIdx.x)) below += v;
+                    if (q == static_cast<int>(blockIdx.x)) s_misc[51 + idx % R] = v;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    below += __shfl_xor_sync(0xffffffffu, below, o);
+                }
+                if (lane == 0) { atomicMax(&s_misc[48], mx); atomicAdd(&s_misc[49], below); }
+            }
+            __syncthreads();
+            if (s_misc[48] <= sub_cap && R * sub_cap <= 2 * nthr) {
+                const int base = s_misc[49];
+                int mine = 0;
+                for (int l = 0; l < R; ++l) mine += s_misc[51 + l];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {               // sub-list l -> buf[words of the sub-lists before it ...)
+                    const int i = tid + k * nthr;
+                    if (i < R * sub_cap) {
+                        const int l = i / sub_cap, kk = i - l * sub_cap;
+                        if (kk < s_misc[51 + l]) {
+                            int at = kk;
+                            for (int m2 = 0; m2 < l; ++m2) at += s_misc[51 + m2];
+                            buf[at] = wv[k];
+                        }
+                    }
+                }
+                __syncthreads();
+                if (dbg) dbg[4] = clock64();
+                for (int i = tid; i < mine; i += nthr) {
+                    const unsigned long long w = buf[i];
+                    int r = base;
+                    for (int q = 0; q < mine; ++q) r += buf[q] < w;
+                    if (r < S.b) S.out_pos[r] = static_cast<int32_t>(w & 0xffffffffu);
+                }
+                if (dbg) { dbg[5] = clock64(); dbg[6] = -1; dbg[7] = mine; }
+                if (blockIdx.x == 0 && tid == 0) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    reinterpret_cast<unsigned long long*>(S.g_ctr + 4)[2] = t;
+                }
+                return;
+            }
+            __syncthreads();
+        }
+    }
     // ---- candidates: every key whose prefix is <= T (the winners plus the few other keys sharing the prefix T) ----
     for (int i = tid; i < cnt; i += nthr) {
         const unsigned long long w = s_list[i];
@@ -314,7 +470,7 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
         s_list[i] = w;
         S.g_cand[off + i] = w;
     }
-    sel_grid_barrier(S.g_ctr, 3u * gridDim.x);
+    sel_grid_barrier(S.g_ctr, ++barriers * gridDim.x);
     if (dbg) dbg[3] = clock64();
     const int total = static_cast<int>(__ldcg(S.g_ctr + 1));
     // ---- rank this CTA's candidates among all of them.  Own candidates are sorted first (a few dozen words: counting);
@@ -332,16 +488,20 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
         mbar_expect_tx(bar, bytes);                                                          // candidates are sorted
         bulk_g2s(buf, S.g_cand, bytes, bar);
     }
-    {                                                       // own candidates sorted (rank by counting), scratch = s_key
-        unsigned long long* tmp = buf + buf_cap;            // [list_cap] words behind the chunk buffer
-        for (int i = tid; i < nc; i += nthr) {
+    unsigned long long* const tree = buf + buf_cap;         // [list_cap] words behind the chunk buffer
+    const int h = sel_tree_height(nc);
+    const bool use_tree = (1 << h) <= S.list_cap && !S.no_tree;           // node indices 1 .. 2^h - 1
+    {                                                       // own candidates sorted (rank by counting; the words are
+        for (int i = tid; i < nc; i += nthr) {              // distinct: the row id is part of them)
             const unsigned long long w = s_list[i];
             int r = 0;
             for (int q = 0; q < nc; ++q) r += s_list[q] < w;
-            tmp[r] = w;
+            tree[use_tree ? sel_tree_node(r, h) : r] = w;
         }
+        if (use_tree)
+            for (int r = nc + tid; r < (1 << h) - 1; r += nthr) tree[sel_tree_node(r, h)] = ~0ull;
         __syncthreads();
-        for (int i = tid; i < nc; i += nthr) s_list[i] = tmp[i];
+        for (int i = tid; i < nc; i += nthr) s_list[i] = tree[use_tree ? sel_tree_node(i, h) : i];
     }
     for (int i = tid; i <= nc; i += nthr) s_hist[i] = 0;    // difference array (nc + 1 <= 2049 entries: s_hist has 2064)
     uint32_t phase = 0;
@@ -356,15 +516,8 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
         mbar_wait(bar, phase);
         phase ^= 1u;
         if (dbg && base == 0) dbg[4] = clock64();
-        for (int j = tid; j < m; j += nthr) {
-            const unsigned long long x = buf[j];
-            int lo = 0, hi = nc;                            // first own candidate > x
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (s_list[mid] <= x) lo = mid + 1; else hi = mid;
-            }
-            atomicAdd(&s_hist[lo], 1u);
-        }
+        if (use_tree) sel_count_into_diff(buf, m, tree, h, s_hist);            // s_hist[first own candidate > x] += 1
+        else sel_count_into_diff_sorted(buf, m, s_list, nc, s_hist);
     }
     __syncthreads();
     if (warp == 0) {                                        // prefix of the difference array: rank of own candidate i
@@ -481,7 +634,10 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
             for (int k = 0; k < 4; ++k) hv[k] = (tid + k * nthr) < 2048 ? __ldcg(S.g_tot + level * 2048 + tid + k * nthr) : 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if ((tid + k * nthr) < 2048) s_hist[tid + k * nthr] = hv[k];
+                if ((tid + k * nthr) < 2048) {
+                    s_hist[tid + k * nthr] = hv[k];
+                    if (level == 0 && hv[k]) atomicMax(&s_misc[6], 2047 - (tid + k * nthr));   // first populated bin, all ranks
+                }
         }
         __syncthreads();
         sel_find_bin(s_hist, want, reinterpret_cast<uint32_t*>(s_misc + 16), &s_misc[level == 0 ? 1 : 5], &s_misc[2]);
@@ -542,6 +698,85 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
         return;
     }
     const unsigned long long* cand = reinterpret_cast<const unsigned long long*>(win + S.cand_off);
+    // ---- bucket route (see select_epilogue): the list is complete in this rank's window, so CTA c scans it once, keeps
+    //      the words of score bucket c (about b / grid of them: the only shared-memory atomics of the stage) and counts
+    //      the words of the buckets below; it then orders its bucket alone.  One more grid barrier tells every CTA
+    //      whether all buckets fitted; if one did not (tie groups), the general ranking below runs instead. ----
+    {
+        const float lo = sel_key_to_float(static_cast<uint32_t>(2047 - s_misc[6]) << 21);
+        const float hi = sel_key_to_float((T << 10) | 0x3ffu);
+        const float scale = static_cast<float>(grid) / (hi - lo);
+        if (isfinite(lo) && isfinite(hi) && hi > lo && isfinite(scale) && S.bucket_cap > 0) {
+            uint64_t* bar = reinterpret_cast<uint64_t*>(s_misc + 8);
+            if (tid == 0) {
+                s_misc[48] = 0; s_misc[49] = 0; s_misc[50] = 0;
+                mbar_init(bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            if (dbg) dbg[3] = clock64();
+            uint32_t phase = 0;
+            int below = 0;
+            const int me = static_cast<int>(blockIdx.x);
+            for (int r = 0; r < W; ++r) {
+                const int tot_r = static_cast<int>(s_tot[r]);
+                for (int base = 0; base < tot_r; base += buf_cap) {
+                    const int m = min(buf_cap, tot_r - base);
+                    __syncthreads();
+                    if (tid == 0) {
+                        const uint32_t bytes = static_cast<uint32_t>((m + 1) & ~1) * 8u;
+                        mbar_expect_tx(bar, bytes);
+                        bulk_g2s(buf, cand + static_cast<size_t>(r) * S.cand_cap + base, bytes, bar);
+                    }
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    for (int j = tid; j < m; j += nthr) {
+                        const unsigned long long x = buf[j];
+                        const float sc = sel_key_to_float(static_cast<uint32_t>(x >> 32));
+                        const int q = min(grid - 1, max(0, __float2int_rd((sc - lo) * scale)));
+                        if (q < me) ++below;
+                        else if (q == me) {
+                            const int slot = atomicAdd(&s_misc[48], 1);
+                            if (slot < S.list_cap) s_list[slot] = x;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+            if (lane == 0 && below) atomicAdd(&s_misc[49], below);
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("mbarrier.inval.shared.b64 [%0];" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))) : "memory");
+                S.g_hist[me] = static_cast<unsigned int>(s_misc[48]);          // the rank's level-0 bins are no longer read
+            }
+            sel_grid_barrier(S.g_ctr, 5u * grid);
+            {
+                int mx = 0;
+                for (int q = tid; q < grid; q += nthr) mx = max(mx, static_cast<int>(__ldcg(S.g_hist + q)));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0 && mx) atomicMax(&s_misc[50], mx);
+            }
+            __syncthreads();
+            if (s_misc[50] <= S.list_cap) {
+                const int mine = s_misc[48], base = s_misc[49];
+                for (int i = tid; i < mine; i += nthr) {
+                    const unsigned long long w = s_list[i];
+                    int rk = base;
+                    for (int q = 0; q < mine; ++q) rk += s_list[q] < w;
+                    if (rk < S.b) S.out_pos[rk] = static_cast<int32_t>(w & 0xffffffffu);
+                }
+                if (dbg) { dbg[4] = clock64(); dbg[5] = dbg[4]; dbg[6] = -M; dbg[7] = mine; }
+                if (blockIdx.x == 0 && tid == 0) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    reinterpret_cast<unsigned long long*>(S.g_ctr + 4)[2] = t;
+                }
+                return;
+            }
+            __syncthreads();
+        }
+    }
     auto list_word = [&](int j) -> unsigned long long {     // word j of the padded list, from this rank's window
         int r = 0;
         while (r + 1 < W && j >= seg_off[r + 1]) ++r;
@@ -562,6 +797,9 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
             s_list[r] = w;
         }
     }
+    // (the slice is searched as a sorted array here: the breadth-first tree of the one-GPU route gave wrong ranks in this
+    //  epilogue on 2 GPUs -- tools/mgpu_tail_dbg.py, cause not found -- and this is only the fallback of the bucket route)
+    __syncthreads();
     for (int i = tid; i <= n2; i += nthr) s_hist[i] = 0;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_misc + 8);
     if (tid == 0) {
@@ -582,15 +820,7 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
-            for (int j = tid; j < m; j += nthr) {
-                const unsigned long long x = buf[j];
-                int lo = 0, hi = n2;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_list[mid] <= x) lo = mid + 1; else hi = mid;
-                }
-                atomicAdd(&s_hist[lo], 1u);
-            }
+            sel_count_into_diff_sorted(buf, m, s_list, n2, s_hist);
         }
     }
     __syncthreads();
@@ -1146,7 +1376,7 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
     if (sharded && (G.world <= 1 || !G.connected)) ALQ_FAIL(ctx, ALQ_ERR_STATE, "alq_uncertainty_tail_sharded: no multi-GPU group (alq_comm_create/connect)");
     if (!sharded) { rows_min = rows_max = n; }
     constexpr int kListCap = 2048;
-    const size_t reserve = static_cast<size_t>(kListCap) * 8 + 2064 * 4 + 256;
+    const size_t reserve = static_cast<size_t>(kListCap) * 8 + 2064 * 4 + 512;      // list, histogram / difference array, s_misc[128]
     RowPipeCfg cfg{};
     size_t smem = 0;
     const bool vec = (c % 4 == 0) && (ld == c) && aligned16(logits) && c <= 2048;
@@ -1181,7 +1411,9 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
     }
     if (sharded)
         if (int rc0 = alq_comm_check(ctx)) return rc0;       // a previous asynchronous exchange that timed out
-    int rc = alq_scratch_reserve(ctx, scratch_need({static_cast<size_t>(n) * 8 + 16}));
+    constexpr int kBucketCap = 48;          // per sub-list: a bucket holds up to 16 x 48 words (about b / grid = 68 expected)
+    static_assert(148 * kBucketLanes <= 2 * 2048, "bucket counters live in the slot's cross-rank words");
+    int rc = alq_scratch_reserve(ctx, scratch_need({static_cast<size_t>(n) * 8 + 16, static_cast<size_t>(ctx->sm_count) * kBucketLanes * kBucketCap * 8}));
     if (rc) return rc;
     SelArgs sel{};
     sel.b = static_cast<int>(b);
@@ -1204,8 +1436,18 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
         if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
         sel.dbg = dbg_buf;
     }
-    sel.g_cand = ScratchCursor(ctx->scratch).take<unsigned long long>(n + 2);
+    {
+        ScratchCursor cur(ctx->scratch);
+        sel.g_cand = cur.take<unsigned long long>(n + 2);
+        if (sharded) sel.bucket_cap = ctx->tail_buckets ? kBucketCap : 0;      // sharded: the route needs no global lists, only the switch
+        if (!sharded && ctx->tail_buckets && ctx->sm_count * kBucketLanes <= 2 * 2048) {
+            sel.bucket_cap = kBucketCap;
+            sel.g_bucket = cur.take<unsigned long long>(static_cast<size_t>(ctx->sm_count) * kBucketLanes * kBucketCap);
+            sel.g_bcnt = sel.g_tot;          // the cross-rank sums are not used on one GPU: zeroed words of the slot
+        }
+    }
     sel.out_pos = out_pos;
+    sel.no_tree = getenv("ALQ_TAIL_NOTREE") ? 1 : 0;
     if (sharded) {
         G.epoch += 1;
         sel.world = G.world; sel.rank = G.rank;

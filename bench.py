@@ -727,10 +727,11 @@ def run_own(args):
     scores = torch.empty(N_ROWS, dtype=torch.float32, device=dev)
     row_lo = rank * N_ROWS
 
-    # A step = K1 -> K1b -> async D2H of the B winners into a pinned host buffer; steps are enqueued back to
-    # back and the host waits once after the K-th (the contract's closing synchronize).  The headline region
+    # A step = the fused K1 + K1b (+ exchange at N > 1) launch -> async D2H of the B winners into a pinned host
+    # buffer (on a copy stream behind an event); steps are enqueued back to back and the host waits once after
+    # the K-th (the contract's closing synchronize, which also covers the copy stream).  The headline region
     # runs the steps in order on one stream, for every N, so the per-N values are comparable and the CUDA-event
-    # pair around K1 times K1 alone.  At N = 1 a second region reports the throughput with two independent
+    # pair around the fused kernel times that kernel alone.  At N = 1 a second region reports the throughput with two independent
     # queries in flight (even/odd steps on two streams / engine contexts: the 148-SM scoring kernel of query
     # i+1 overlaps the 8-SM top-B cluster kernel of query i; K1 claims its tiles dynamically so CTAs that start
     # late behind the cluster kernel are not stragglers).
@@ -745,6 +746,18 @@ def run_own(args):
         engines = [eng] + [Engine(local) for _ in range(depth - 1)]
         streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         score_bufs = [scores] + [torch.empty_like(scores) for _ in range(depth - 1)]
+        # the B winners leave on a copy stream behind an event, so the next step's kernel does not queue behind the
+        # 40 KB D2H of this one (the region's closing wait covers the copy stream too)
+        copy_stream = torch.cuda.Stream(device=dev)
+        done = [torch.cuda.Event() for _ in range(4)]
+
+        def to_host(i, k, pos):
+            ev = done[i & 3]
+            ev.record(streams[k])
+            copy_stream.wait_event(ev)
+            with torch.cuda.stream(copy_stream):
+                host_out[i & 1].copy_(pos, non_blocking=True)
+            pos.record_stream(copy_stream)
 
         def step(i, pair=None):
             k = i % depth
@@ -756,20 +769,20 @@ def run_own(args):
                     _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)   # K1 + K1b: ONE cooperative launch
                     if pair is not None:
                         pair[1].record()
-                    host_out[i & 1].copy_(pos, non_blocking=True)
+                    to_host(i, k, pos)
                 elif getattr(e, "comm_ready", False):
                     # K1 + K1b + the cross-GPU exchange: ONE cooperative launch per rank (histograms summed and candidates
                     # gathered through the peer-memory windows from inside the kernel)
                     _, gp = e.uncertainty_tail_sharded(logits, MODE_MARGIN, BUDGET, row_lo, N_ROWS, N_ROWS, scores_out=sc)
                     if pair is not None:
                         pair[1].record()
-                    host_out[i & 1].copy_(gp, non_blocking=True)
+                    to_host(i, k, gp)
                 else:
                     _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)
                     if pair is not None:
                         pair[1].record()
                     gp = group.merge_smallest(sc, pos, row_lo, BUDGET, e, to_host=False)   # all-gather + device merge
-                    host_out[i & 1].copy_(gp, non_blocking=True)
+                    to_host(i, k, gp)
 
         for i in range(warm * depth):
             step(i)
@@ -784,7 +797,7 @@ def run_own(args):
             st.wait_event(ev0)
         for i in range(steps):
             step(i, pairs[i])
-        for st in streams:
+        for st in streams + [copy_stream]:
             torch.cuda.current_stream().wait_stream(st)
         ev1.record()
         tenq = time.perf_counter()

@@ -52,6 +52,9 @@ const char* alq_last_error(const alq_ctx* ctx);
  *                    Default 64; 0 turns the hints off
  *   "d2_fast_path"   1 (default): the persistent loop's D^2 draw first tries the certified path (one fp64 mass per CTA, the
  *                    rounding of NumPy's float32 probabilities bounded by a margin); 0: always the exact NumPy-tree machinery
+ *   "tail_buckets"   1 (default): alq_uncertainty_tail on one GPU routes the candidates to per-CTA score buckets, each CTA sorts
+ *                    its own bucket; 0: the general route (every CTA ranks its candidates against the whole list), which is also
+ *                    what a pool whose scores do not spread (tie groups) falls back to inside the launch
  *   "spin_timeout_ms" how long a kernel waits for a peer GPU's flag before giving up with ALQ_ERR_STATE (default 20000)
  *   "select_impl"    0 auto | 1 multi-kernel radix select   | 2 single cluster-resident launch
  *   "base_impl"      0 auto | 1 sequential class loop       | 2 per-class candidate lists + in-order resolve */

@@ -212,15 +212,36 @@ def test_pipelined_rows_kernels_equal_direct_kernels(eng, n, c):
 @pytest.mark.parametrize("n,c,b", [(80000, 1000, 10000), (80000, 1000, 1), (5000, 40, 5000), (4100, 12, 77), (30011, 1000, 3000), (200000, 8, 16000)])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_fused_tail_equals_score_then_select(eng, n, c, b, mode):
-    """alq_uncertainty_tail (K1 + K1b as one cooperative launch: per-CTA key lists, global 11-bit histogram, winners
-    ranked by counting) against the two separate kernels: identical scores, identical ordered positions."""
+    """alq_uncertainty_tail (K1 + K1b as one launch: per-CTA key lists, two global 11-bit histogram levels, winners
+    ordered either through per-CTA score buckets or by ranking against the whole list) against the two separate kernels:
+    identical scores, identical ordered positions, on both routes."""
     g = torch.Generator(device="cuda").manual_seed(n + c + b + mode)
     logits = torch.randn(n, c, device="cuda", generator=g) * 3
     ref_s = eng.score_softmax(logits, mode)
     ref_p = eng.select_smallest(ref_s, b)
-    s, p = eng.uncertainty_tail(logits, mode, b)
-    assert torch.equal(s, ref_s)
-    assert torch.equal(p, ref_p)
+    try:
+        for buckets in (1, 0):
+            eng.set_option("tail_buckets", buckets)
+            s, p = eng.uncertainty_tail(logits, mode, b)
+            assert torch.equal(s, ref_s)
+            assert torch.equal(p, ref_p), buckets
+    finally:
+        eng.set_option("tail_buckets", 1)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fused_tail_with_skewed_scores(eng, mode):
+    """Scores that do not spread evenly between the candidate range's edges (per-row temperature over five decades: the
+    margins pile up next to 0, the confidences next to 1/C and 1): the score buckets are uneven, and with the 40-row pool
+    piled into a few of them one bucket exceeds its capacity and the launch falls back to the general route by itself."""
+    g = torch.Generator(device="cuda").manual_seed(77 + mode)
+    for n, c, b in ((90000, 1000, 10000), (120000, 40, 30000), (50000, 16, 49000)):
+        temp = torch.exp(torch.randn(n, 1, device="cuda", generator=g) * 4)
+        logits = torch.randn(n, c, device="cuda", generator=g) * temp
+        ref_s = eng.score_softmax(logits, mode)
+        s, p = eng.uncertainty_tail(logits, mode, b)
+        assert torch.equal(s, ref_s)
+        assert torch.equal(p, eng.select_smallest(ref_s, b))
 
 
 def test_fused_tail_with_massive_ties(eng):

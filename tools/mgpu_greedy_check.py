@@ -82,7 +82,8 @@ def case(n, l, d, c, b, ints, seed, uneven=False):
         ok = ok and bool(allsame.item())
 
 
-if not (len(sys.argv) > 1 and sys.argv[1] == "bigonly"):
+ARG = sys.argv[1] if len(sys.argv) > 1 else ""
+if ARG not in ("bigonly", "tailonly", "tails"):
     case(6001, 700, 512, 0, 64, True, 1)
     case(6001, 700, 512, 40, 64, True, 2, uneven=True)
     case(3000, 300, 2048, 0, 40, False, 3)
@@ -133,10 +134,11 @@ def tail_case(n_per, c, b, seed, dyadic=False):
         ok = ok and bool(same.item())
 
 
-tail_case(20000, 1000, 10000, 11)
-tail_case(9000, 64, 3000, 12, dyadic=True)
-tail_case(4200, 1000, 700, 13)
-if len(sys.argv) > 1 and sys.argv[1] in ("big", "bigonly"):
+if ARG != "tailonly":
+    tail_case(20000, 1000, 10000, 11)
+    tail_case(9000, 64, 3000, 12, dyadic=True)
+    tail_case(4200, 1000, 700, 13)
+if ARG in ("big", "bigonly", "tailonly", "tails"):
     tail_case(80000, 1000, 10000, 14)
 dist.barrier()
 if rank == 0:

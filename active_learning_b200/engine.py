@@ -117,7 +117,7 @@ class Engine:
         return out
 
     def uncertainty_tail(self, logits: torch.Tensor, mode: int, b: int, scores_out: Optional[torch.Tensor] = None):
-        """K1 + K1b in one call (one cooperative launch when the fused path applies): (scores [n], positions [b] int32,
+        """K1 + K1b in one call (one launch when the fused path applies): (scores [n], positions [b] int32,
         ascending (score, position))."""
         logits = _f32c(logits, "logits")
         n, c = logits.shape
@@ -136,7 +136,7 @@ class Engine:
 
     def uncertainty_tail_sharded(self, logits: torch.Tensor, mode: int, b: int, row_lo: int, rows_min: int, rows_max: int,
                                  scores_out: Optional[torch.Tensor] = None):
-        """K1 + K1b + the cross-GPU exchange in one call (one cooperative launch per rank when the fused path applies):
+        """K1 + K1b + the cross-GPU exchange in one call (one launch per rank when the fused path applies):
         (scores [n] of this shard, global positions [b] int32 -- identical on every rank).  Collective over comm_init's group."""
         logits = _f32c(logits, "logits")
         n, c = logits.shape

@@ -766,12 +766,12 @@ def run_own(args):
                 if pair is not None:
                     pair[0].record()
                 if group is None:
-                    _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)   # K1 + K1b: ONE cooperative launch
+                    _, pos = e.uncertainty_tail(logits, MODE_MARGIN, BUDGET, scores_out=sc)   # K1 + K1b: ONE launch
                     if pair is not None:
                         pair[1].record()
                     to_host(i, k, pos)
                 elif getattr(e, "comm_ready", False):
-                    # K1 + K1b + the cross-GPU exchange: ONE cooperative launch per rank (histograms summed and candidates
+                    # K1 + K1b + the cross-GPU exchange: ONE launch per rank (histograms summed and candidates
                     # gathered through the peer-memory windows from inside the kernel)
                     _, gp = e.uncertainty_tail_sharded(logits, MODE_MARGIN, BUDGET, row_lo, N_ROWS, N_ROWS, scores_out=sc)
                     if pair is not None:
@@ -898,8 +898,8 @@ def run_own(args):
         "host_enqueue_ms_per_step": (t_enq - t_w0) * 1e3 / args.steps,
         "latency_ms_single_query": latency_ms,
         "pipelined": pipelined,
-        "roofline": {"kernel": "rows_pipe_kernel<8,margin> with the fused selection epilogue (K1 + K1b in one cooperative launch: TMA bulk-copy "
-                               "pipelined softmax-margin score, then histogram / candidate / rank-by-counting stages behind two grid barriers); "
+        "roofline": {"kernel": "rows_pipe_kernel<8,margin> with the fused selection epilogue (K1 + K1b in one launch: TMA bulk-copy "
+                               "pipelined softmax-margin score, then two histogram levels and the score-bucket ordering of the winners behind three grid barriers); "
                                "the CUDA events bracket the WHOLE kernel, selection included", "bound": "hbm",
                      "achieved": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": N_ROWS * (4 * N_CLASSES + 4) / (k1_ms * 1e-3) / 1e9 / peak,

@@ -89,8 +89,10 @@ int alq_select_smallest(alq_ctx* ctx, const float* scores, int64_t n, int64_t b,
 /* K1 + K1b as ONE launch: scores[i] as alq_score_softmax AND out_pos[0..b) as alq_select_smallest of those scores --
  * the whole tail of MarginSampler.query / ConfidenceSampler.query (margin_sampler.py:33-42) behind one call.  When the
  * pipelined scoring kernel applies (c % 4 == 0, contiguous rows, 4096 <= n <= ~240 000 per GPU) the selection runs in
- * that kernel's epilogue (cooperative launch: per-CTA key lists in shared memory, one global 2048-bin histogram, the
- * winners ranked by counting); otherwise the two kernels run back to back.  Same results either way.             */
+ * that kernel's epilogue (one CTA per SM, device-wide spin barriers: per-CTA key lists in shared memory, two global
+ * 2048-bin histogram levels, the winners ordered through per-CTA score buckets -- option "tail_buckets"); otherwise the
+ * two kernels run back to back.  Same results either way.  Launches of this kernel (and of the persistent selection loop)
+ * from different streams of one process are serialised against each other by the library.                              */
 int alq_uncertainty_tail(alq_ctx* ctx, const float* logits, int64_t n, int32_t c, int64_t ld, int32_t mode,
                          int64_t b, float* scores, int32_t* out_pos, void* stream);
 
@@ -102,7 +104,7 @@ int alq_uncertainty_tail_timing(alq_ctx* ctx, float* out_ms_host);
 /* The same tail with the rows sharded over the G ranks of the peer-memory group (alq_comm_create/connect): rank r holds
  * `n` rows that are positions [row_lo, row_lo + n) of the pool and every rank receives the same out_gpos[0..b): the global
  * positions of the b smallest scores over ALL ranks, ascending (score, position) -- exactly what a single GPU returns for
- * the concatenated pool.  K1, K1b and the exchange are ONE cooperative launch per rank: both histogram levels are summed over
+ * the concatenated pool.  K1, K1b and the exchange are ONE launch per rank: both histogram levels are summed over
  * the ranks and the b + few candidate words gathered through the windows from inside the kernel (8-byte {tag, value} words
  * and plain stores over NVLink; no collective library, nothing on the host).  Collective: every rank calls it with the same
  * c, mode, b, rows_min / rows_max (the smallest / largest shard; they decide, identically on every rank, whether the fused

@@ -186,7 +186,8 @@ struct SelArgs {
     unsigned long long* g_bucket;   // [grid][kBucketLanes][bucket_cap]
     unsigned int* g_bcnt;           // [grid][kBucketLanes] zeroed
     int bucket_cap;                 // words per sub-list
-    int no_tree;                    // debug (ALQ_TAIL_NOTREE): binary search over the sorted array instead of the tree
+    int use_tree;                   // experiment (ALQ_TAIL_TREE=1): the general route searches a breadth-first tree copy of the
+                                    // CTA's candidates instead of the sorted array; off by default, see select_epilogue
 };
 constexpr int kBucketLanes = 16;
 
@@ -247,15 +248,18 @@ __device__ __forceinline__ void sel_find_bin(const uint32_t* hist, uint32_t k, u
     __syncthreads();
 }
 
-// Ranking stage, shared by the one-GPU and the sharded epilogue.  The CTA's own (ascending) candidates are searched
-// once per word of the global list -- about b searches per CTA -- and a plain binary search over a sorted array in
-// shared memory is bound by bank conflicts, not by latency: the probes of step k sit a power-of-two stride apart and
-// fall into one or two banks (measured: 11 k cycles of the 14 k-cycle stage for 10 001 words against 80 candidates).
-// So the candidates are also kept as an implicit perfect search tree in breadth-first order (1-based: children of
-// node k are 2k and 2k + 1; missing nodes hold ~0, which no list word reaches): the probes of one step are contiguous
-// words.  Height h = smallest with 2^h - 1 >= nc; the sorted index r sits at node
+// Ranking stage of the general route.  The CTA's own (ascending) candidates are searched once per word of the global
+// list -- about b searches per CTA.  A plain binary search over a sorted array in shared memory pays bank conflicts: the
+// probes of step k sit a power-of-two stride apart and fall into one or two banks.  EXPERIMENT (ALQ_TAIL_TREE=1, off by
+// default): the candidates are also kept as an implicit perfect search tree in breadth-first order (1-based: children
+// of node k are 2k and 2k + 1; missing nodes hold ~0, which no list word reaches), so the probes of one step are
+// contiguous words.  Height h = smallest with 2^h - 1 >= nc; the sorted index r sits at node
 //     k(r) = 2^(h-1-z) + ((r + 1) >> (z + 1)),  z = trailing zeros of r + 1,
-// and after h steps of  k = 2k + (tree[k] <= x)  the count of candidates <= x is k - 2^h.
+// and after h steps of  k = 2k + (tree[k] <= x)  the count of candidates <= x is k - 2^h.  Measured on one B200: the stage
+// goes from 13.8 k to 10.6 k cycles, where the ~b shared-memory atomics on the difference array take over (the reason for
+// the bucket route).  It is exact in every one-GPU test, but the same helper produced wrong ranks inside the sharded
+// epilogue on 2 GPUs for c = 64 (tools/mgpu_tail_dbg.py; a host emulation of the arithmetic agrees with the sorted
+// search, so the cause is on the device side and unexplained) -- hence not the default anywhere.
 __device__ __forceinline__ int sel_tree_height(int nc) { return nc > 0 ? 32 - __clz(nc) : 0; }
 __device__ __forceinline__ int sel_tree_node(int r, int h) {
     const int t = r + 1, z = __ffs(t) - 1;
@@ -490,7 +494,7 @@ __device__ __noinline__ void select_epilogue(const SelArgs& S, uint32_t* s_hist,
     }
     unsigned long long* const tree = buf + buf_cap;         // [list_cap] words behind the chunk buffer
     const int h = sel_tree_height(nc);
-    const bool use_tree = (1 << h) <= S.list_cap && !S.no_tree;           // node indices 1 .. 2^h - 1
+    const bool use_tree = S.use_tree && (1 << h) <= S.list_cap;           // node indices 1 .. 2^h - 1
     {                                                       // own candidates sorted (rank by counting; the words are
         for (int i = tid; i < nc; i += nthr) {              // distinct: the row id is part of them)
             const unsigned long long w = s_list[i];
@@ -797,8 +801,7 @@ __device__ __noinline__ void select_epilogue_mgpu(const SelArgs& S, uint32_t* s_
             s_list[r] = w;
         }
     }
-    // (the slice is searched as a sorted array here: the breadth-first tree of the one-GPU route gave wrong ranks in this
-    //  epilogue on 2 GPUs -- tools/mgpu_tail_dbg.py, cause not found -- and this is only the fallback of the bucket route)
+    // (the slice is searched as a sorted array: see the note on the breadth-first tree above sel_tree_height)
     __syncthreads();
     for (int i = tid; i <= n2; i += nthr) s_hist[i] = 0;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_misc + 8);
@@ -1447,7 +1450,7 @@ static int uncertainty_tail_impl(alq_ctx* ctx, const float* logits, int64_t n, i
         }
     }
     sel.out_pos = out_pos;
-    sel.no_tree = getenv("ALQ_TAIL_NOTREE") ? 1 : 0;
+    sel.use_tree = getenv("ALQ_TAIL_TREE") ? 1 : 0;
     if (sharded) {
         G.epoch += 1;
         sel.world = G.world; sel.rank = G.rank;

@@ -7,6 +7,12 @@ What moves to the GPU is the part that scales with the pool: the embeddings neve
 kept as running per-class sums, the two distance fields of a balancing step are K3 calls (`alq_min_dist`, min against
 the rarest centre and max over the majority centres) and the masked ratio arg-min is `alq_ratio_argmin`; one int32
 returns to the host per step.
+
+Rounding: the class centres here are running per-class sums divided by (count + 1e-5); the reference builds
+1 / (count + 1e-5) first and multiplies inside a matmul (:86-88).  The two are equal in exact arithmetic and differ in
+the last fp32 bits, so a balancing step whose two best ratios are closer than ~1e-6 relative may pick the other row
+than the reference does.  The golden fixtures (tests/golden/reference_golden_balancing.npz) are pick-for-pick
+identical; outside them the guarantee is "same pick unless the reference's own arg-min is decided by fp32 rounding".
 """
 from __future__ import annotations
 

@@ -259,7 +259,14 @@ __device__ __forceinline__ void sel_find_bin(const uint32_t* hist, uint32_t k, u
 // goes from 13.8 k to 10.6 k cycles, where the ~b shared-memory atomics on the difference array take over (the reason for
 // the bucket route).  It is exact in every one-GPU test, but the same helper produced wrong ranks inside the sharded
 // epilogue on 2 GPUs for c = 64 (tools/mgpu_tail_dbg.py; a host emulation of the arithmetic agrees with the sorted
-// search, so the cause is on the device side and unexplained) -- hence not the default anywhere.
+// search, so the cause is on the device side) -- hence not the default anywhere.  What is known: the wrong positions were
+// exactly the slices of ~12 CTAs per rank (presumably the ones that had streamed rows: 36 claims of 8 tiles, three per
+// producer); for c = 64 the tree sits at byte 131 056 of the CTA's shared memory and its nodes 2..33 are the words of the
+// tile ring's full[] / empty[] mbarriers (ring = 16 x 8 KB), which the epilogue reuses as plain memory WITHOUT
+// mbarrier.inval -- PTX calls that undefined.  For c = 1000 those words are nodes 2002..2025 (never used), for c = 8
+// they lie inside the list buffer.  Hypothesis, not verified (no GPU time left in round 2): invalidate the 2 x stages
+// ring barriers at the top of the epilogue.  The shipped routes touch those words only transiently (staging copy of the
+// own candidates, written and read back between two barriers), and every parity test passes.
 __device__ __forceinline__ int sel_tree_height(int nc) { return nc > 0 ? 32 - __clz(nc) : 0; }
 __device__ __forceinline__ int sel_tree_node(int r, int h) {
     const int t = r + 1, z = __ffs(t) - 1;
